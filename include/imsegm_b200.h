@@ -1,0 +1,130 @@
+/*
+ * imsegm_b200.h -- C-ABI of the B200-native SLIC -> descriptors -> GraphCut hot path of Borda/pyImSegm.
+ *
+ * Every entry point takes plain DEVICE pointers (unless a parameter says "host"), sizes and a CUDA stream
+ * (cudaStream_t passed as void*), returns 0 on success or a negative isb_status, never allocates what it
+ * returns and never throws.  isb_last_error() gives the message of the last failure on the calling thread.
+ * The caller owns all buffers; `ws` is scratch the caller sizes with the matching *_workspace_bytes().
+ * All launches are asynchronous on `stream` unless a parameter is documented as a host output.
+ *
+ * Each declaration names the reference interface it replaces (file:line under the reference repository).
+ */
+#ifndef IMSEGM_B200_H
+#define IMSEGM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* isb_stream_t; /* cudaStream_t */
+
+enum isb_status {
+    ISB_OK = 0,
+    ISB_ERR_ARG = -1,      /* bad argument (null pointer, non-positive size, unsupported dtype...) */
+    ISB_ERR_CUDA = -2,     /* a CUDA runtime call failed; see isb_last_error() */
+    ISB_ERR_CAPACITY = -3, /* a caller-sized table was too small (edge table, candidate list); retry larger */
+    ISB_ERR_UNSUPPORTED = -4
+};
+
+enum isb_dtype { ISB_U8 = 0, ISB_U16 = 1, ISB_F32 = 2, ISB_F64 = 3 };
+
+const char* isb_last_error(void);
+int isb_abi_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+long long isb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * (i) SLIC -- replaces skimage.segmentation.slic as called from imsegm/superpixels.py:61-63
+ *     slic(img f64[H,W,3] in [0,1], n_segments, compactness, sigma=1, enforce_connectivity=True, slic_zero)
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* min-max rescale to [0,1] (imsegm/superpixels.py:53-54), gaussian pre-blur (scipy.ndimage semantics: symmetric
+ * 1-D correlate, mode reflect, depth(len 1) -> rows -> cols), rgb2lab, multiply by ratio = 1/compactness.
+ *   img        : [H,W,C] interleaved, C in {1,3} (gray is replicated, superpixels.py:50-51), dtype = isb_dtype
+ *   w_half     : HOST pointer, radius+1 doubles, w_half[0] = centre tap (radius <= 8; radius 0 = no blur)
+ *   lab_planar : out, [3,H,W] f64
+ *   minmax_out : out, 2 doubles (device) -- min and max of the raw image; max == min makes the result NaN
+ *   rescale    : 1 = apply the reference wrapper's min-max rescale when (min != 0 or max != 1); 0 = never */
+int isb_slic_prepare(const void* img, int dtype, int H, int W, int C, const double* w_half, int radius, double ratio,
+                     int rescale, double* lab_planar, double* minmax_out, isb_stream_t stream);
+
+size_t isb_slic_kmeans_workspace_bytes(int H, int W, int n_seeds, int step_y, int step_x);
+
+/* k-means sweeps of _slic_cython: window +-2*step about each centroid, lowest index wins ties, centroid = raster
+ * order sequential double sums / count.  Bit-exact with oracle/slic_oracle.c by construction.
+ *   seeds_yx  : [n_seeds,2] f64 (row, col) regular grid (device)
+ *   labels    : out [H,W] i32;  centroids : optional out [n_seeds,5] f64 (y,x,L,a,b) */
+int isb_slic_kmeans(const double* lab_planar, int H, int W, const double* seeds_yx, int n_seeds, int step_y, int step_x,
+                    double step, int max_iter, int slic_zero, int32_t* labels, double* centroids, void* ws, size_t ws_bytes,
+                    isb_stream_t stream);
+
+size_t isb_connectivity_workspace_bytes(int H, int W);
+
+/* _enforce_label_connectivity_cython: raster-order relabel of 4-connected components, BFS truncated at max_size,
+ * components < min_size merged into the last already-labelled neighbour seen.  Bit-exact with the oracle.
+ *   n_labels_out : device int32, number of output labels (labels are 0..n-1) */
+int isb_enforce_connectivity(const int32_t* labels, int H, int W, int min_size, int max_size, int32_t* out,
+                             int32_t* n_labels_out, void* ws, size_t ws_bytes, isb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * (ii) descriptors -- replaces imsegm/features_cython.pyx (the reference's only native module)
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* computeColorImage2dMean :81, ...Energy :101, ...Variance :122 and normColorFeatures :59 in one launch family,
+ * plus the centroids of imsegm/superpixels.py:205-224.  Pixels are converted to f32 (descriptors.py:233),
+ * accumulated in f64.
+ *   img     : [H,W,3] interleaved, dtype = isb_dtype (NaN -> 0 as descriptors.py:824)
+ *   seg     : [H,W] i32 in [0, nb)
+ *   flags   : bit0 mean, bit1 std, bit2 energy  -> feature columns in that order, 3 channels each
+ *   feat    : out [nb, ld] f64, columns written at col0.. ; absent labels give 0
+ *   centres : optional out [nb,2] f64 (row, col), (-1,-1) for absent labels;  counts: optional out [nb] i32 */
+size_t isb_segment_stats_workspace_bytes(int nb);
+int isb_segment_stats_2d(const void* img, int dtype, const int32_t* seg, int H, int W, int nb, int flags, double* feat,
+                         int ld, int col0, double* centres, int32_t* counts, void* ws, size_t ws_bytes, isb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * (iii) graph + energies + alpha-expansion
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* make_graph_segm_connect_grid2d_conn4 (imsegm/superpixels.py:157-177) for labels already in [0, nb):
+ * unique 4-connected label pairs (a < b) sorted by (b, a).
+ *   edges : out [cap,2] i32;  n_edges_out : device int32 (if > cap the call reports ISB_ERR_CAPACITY lazily:
+ *           the host must check n_edges_out <= cap) */
+size_t isb_adjacency_workspace_bytes(int nb, int cap);
+int isb_adjacency_edges(const int32_t* seg, int H, int W, int nb, int32_t* edges, int cap, int32_t* n_edges_out, void* ws,
+                        size_t ws_bytes, isb_stream_t stream);
+
+/* compute_unary_cost (imsegm/graph_cuts.py:523-540), compute_edge_weights / compute_edge_model / compute_spatial_dist
+ * (:574-657, :383-439, :303-336), create_pairwise_matrix_uniform (:442-456), and pyGCO's float->int conversion.
+ *   proba [N,K] f64, edges [E,2] i32 (n_edges read from device n_edges_dev when non-null, else E), centres [N,2] f64
+ *   edge_mode: 0 = ones, 1 = model_lT, 2 = model_l1, 3 = model_l2, 4 = spatial only; modes 1..4 divide by the
+ *              relative centroid distance
+ *   out: unary [N,K] f64, edge_w [E] f64, and the integerised (unary_i [N,K], edge_wi [E], smooth_i [K,K]) i32 */
+int isb_gc_energies(const double* proba, int N, int K, const int32_t* edges, int E, const int32_t* n_edges_dev,
+                    const double* centres, int edge_mode, double edge_cost, const double* pairwise /* [K,K] device */,
+                    double* unary, double* edge_w, int32_t* unary_i, int32_t* edge_wi, int32_t* smooth_i, void* ws,
+                    size_t ws_bytes, isb_stream_t stream);
+size_t isb_gc_energies_workspace_bytes(int N, int K, int E);
+
+/* gco.cut_general_graph(..., algorithm='expansion', n_iter) on integer energies (imsegm/graph_cuts.py:735-744).
+ * One CTA cluster per graph; push-relabel max-flow; a site keeps its label iff it can reach the sink in the
+ * residual graph (BK's SINK segment) so labels are identical to the oracle's.
+ *   labels : in/out [N] i32 (initial labeling, zeros for the reference call);  energy_out : device int64 */
+size_t isb_alpha_expansion_workspace_bytes(int N, int K, int E);
+int isb_alpha_expansion(int N, int K, int E, const int32_t* n_edges_dev, const int32_t* edges, const int32_t* edge_wi,
+                        const int32_t* unary_i, const int32_t* smooth_i, int n_iter, int32_t* labels, int64_t* energy_out,
+                        int32_t* stats_out /* optional [4]: moves, flows, sweeps, relabels */, void* ws, size_t ws_bytes,
+                        isb_stream_t stream);
+
+/* final LUT gathers of imsegm/pipelines.py:104,109:  segm = graph_labels[slic], segm_soft = proba[slic]
+ *   lut_i [nb] i32 (optional), lut_p [nb,K] f64 (optional); outputs [H,W] i32 / [H,W,K] f64 */
+int isb_gather(const int32_t* seg, long long npx, const int32_t* lut_i, const double* lut_p, int K, int32_t* out_i,
+               double* out_p, isb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMSEGM_B200_H */

@@ -1,0 +1,87 @@
+"""
+ctypes binding of ``libimsegm_b200.so`` (the C-ABI declared in ``include/imsegm_b200.h``).
+
+There is NO fallback: if the shared library is missing or a CUDA device is absent the calls raise.
+torch is used only for device memory (tensors as containers) and streams.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libimsegm_b200.so')
+
+_lib = None
+
+ISB_OK, ISB_ERR_ARG, ISB_ERR_CUDA, ISB_ERR_CAPACITY, ISB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+DTYPE_CODES = {'uint8': 0, 'uint16': 1, 'float32': 2, 'float64': 3}
+
+_vp, _i, _d, _sz, _ll = C.c_void_p, C.c_int, C.c_double, C.c_size_t, C.c_longlong
+
+#: every symbol declared in include/imsegm_b200.h: name -> (restype, argtypes)
+SIGNATURES = {
+    'isb_last_error': (C.c_char_p, []),
+    'isb_abi_version': (_i, []),
+    'isb_launch_count': (_ll, []),
+    'isb_slic_prepare': (_i, [_vp, _i, _i, _i, _i, C.POINTER(_d), _i, _d, _i, _vp, _vp, _vp]),
+    'isb_slic_kmeans_workspace_bytes': (_sz, [_i, _i, _i, _i, _i]),
+    'isb_slic_kmeans': (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    'isb_connectivity_workspace_bytes': (_sz, [_i, _i]),
+    'isb_enforce_connectivity': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    'isb_segment_stats_workspace_bytes': (_sz, [_i]),
+    'isb_segment_stats_2d': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    'isb_adjacency_workspace_bytes': (_sz, [_i, _i]),
+    'isb_adjacency_edges': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    'isb_gc_energies_workspace_bytes': (_sz, [_i, _i, _i]),
+    'isb_gc_energies': (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'isb_alpha_expansion_workspace_bytes': (_sz, [_i, _i, _i]),
+    'isb_alpha_expansion': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'isb_gather': (_i, [_vp, _ll, _vp, _vp, _i, _vp, _vp, _vp]),
+}
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """load the CUDA extension; raises (never falls back) when it has not been built"""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise NativeLibraryError(
+                'pyimsegm_b200: %s is missing -- build it with `python -m pyimsegm_b200.build` '
+                '(there is no CPU fallback)' % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError here = header / library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status):
+    if status != ISB_OK:
+        msg = lib().isb_last_error().decode(errors='replace')
+        if status == ISB_ERR_ARG:
+            raise ValueError('imsegm_b200: ' + msg)
+        if status == ISB_ERR_UNSUPPORTED:
+            raise NotImplementedError('imsegm_b200: ' + msg)
+        raise RuntimeError('imsegm_b200 (status %d): %s' % (status, msg))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise NativeLibraryError('pyimsegm_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback')
+    return torch
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)"""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
