@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""
+bench.py -- megapixels/second through pipe_color2d_slic_features_model_graphcut (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "config 2"): one synthetic 2048x2048 RGB float64 image per
+GPU per step -- Voronoi regions with 3 class means + gaussian noise, sp_size 29 (4 987 seeds), colour-mean descriptors,
+3-class GMM, GraphCut with gc_regul 1 / 'model' edges.  A "step" is one pass of the whole path over that image.
+N > 1 shards independent images over ranks (one process per GPU, weak scaling, no data-path collective).
+
+  value : MPix/s with the image already resident in HBM and results left in HBM (device-resident)
+  e2e   : MPix/s through the public numpy API -- pinned host image in, (segm, segm_soft) host arrays out
+Timed with CUDA events on the launching stream between barrier + synchronize, max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 2048
+SP_SIZE, SP_REGUL, NB_CLASSES, GC_REGUL = 29, 0.2, 3, 1.0
+FEATURES = {'color': ['mean']}
+METRIC = 'megapixels/sec end-to-end SLIC+features+GC (pipe_color2d_slic_features_model_graphcut)'
+WORKLOAD = 'config2: 2048x2048 RGB f64 synthetic, SLIC sp_size=29 (~5k superpixels) + colour-mean + 3-class GMM + GraphCut'
+#: algorithmic bytes per pixel of the dominant kernel (slic_assign): read Lab 3 x f64 + write label i32
+ASSIGN_BYTES_PER_PX = 28
+
+
+def synth_image(seed, h=H, w=W, n_classes=NB_CLASSES, cell=64):
+    rng = np.random.RandomState(seed)
+    pts = rng.rand(40, 2) * [h, w]
+    cls = rng.randint(0, n_classes, 40)
+    gy, gx = np.mgrid[:(h + cell - 1) // cell, :(w + cell - 1) // cell] * cell + cell / 2
+    near = ((gy[..., None] - pts[:, 0]) ** 2 + (gx[..., None] - pts[:, 1]) ** 2).argmin(-1)
+    cl = np.kron(cls[near], np.ones((cell, cell), dtype=int))[:h, :w]
+    means = np.linspace(0.2, 0.8, n_classes)
+    img = means[cl][..., None] + np.array([0.0, 0.03, -0.03])
+    return np.clip(img + rng.normal(0, 0.05, img.shape), 0, 1)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region"""
+    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    return rank, world, local
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU path (oracle port; scikit-image and gco are not installable here) on host cores
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _oracle_one(seed):
+    import oracle
+    from sklearn import mixture, pipeline, preprocessing
+    img = synth_image(seed)
+    t0 = time.perf_counter()
+    slic, fts = oracle.compute_color2d_superpixels_features(img, ('mean',), SP_SIZE, SP_REGUL)
+    nb_inits = max(1, int(np.sqrt(99)))
+    model = pipeline.Pipeline([('std_scaler', preprocessing.StandardScaler()),
+                               ('model', mixture.GaussianMixture(NB_CLASSES, covariance_type='full', n_init=nb_inits, max_iter=99))])
+    model.fit(fts)
+    proba = model.predict_proba(fts)
+    labels = oracle.segment_graph_cut_general(slic, proba, GC_REGUL, 'model')
+    segm, soft = labels[slic], proba[slic]
+    return time.perf_counter() - t0, int(segm.sum() % 7)
+
+
+def cpu_reference_throughput(n_images, workers):
+    """MPix/s of the CPU path over n_images images with `workers` processes (the reference's own Pool idiom,
+    imsegm/utilities/experiments.py:354-410; default workers = int(0.6 * cpu_count), pipelines.py:43)"""
+    import multiprocessing as mp
+    import oracle
+    oracle.build()
+    seeds = list(range(1000, 1000 + n_images))
+    t0 = time.perf_counter()
+    if workers <= 1:
+        res = [_oracle_one(s) for s in seeds]
+    else:
+        with mp.get_context('fork').Pool(workers) as pool:
+            res = pool.map(_oracle_one, seeds)
+    dt = time.perf_counter() - t0
+    return n_images * H * W / 1e6 / dt, dt, res
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = min(64, max(1, int(0.6 * cores)))  # the reference's NB_WORKERS rule, capped to bound host memory
+    n_img = workers  # one bounded sample per step: `workers` images through the process pool
+    for _ in range(args.warmup):
+        cpu_reference_throughput(min(n_img, 2), min(workers, 2))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_throughput(n_img, workers)
+    dt = time.perf_counter() - t0
+    value = args.steps * n_img * H * W / 1e6 / dt
+    sample = '%d step(s) x %d images of 2048x2048 through a %d-process pool (reference idiom: Pool over images)' % (args.steps, n_img, workers)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'MPix/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'sp_size': SP_SIZE, 'nb_classes': NB_CLASSES,
+                   'note': 'CPU restatement of the reference path (oracle/): scikit-image and gco cannot be installed here'},
+        'cpu_baseline': {'value': value, 'unit': 'MPix/s', 'cores': workers, 'kind': 'port', 'sample': sample,
+                         'host_cpus': cores},
+        'e2e': {'value': value, 'unit': 'MPix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback)'
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from pyimsegm_b200 import _lib, pipelines
+    from pyimsegm_b200.graph_cuts import estim_class_model
+    lib = _lib.lib()
+
+    img = synth_image(2 + rank)
+    host_img = torch.from_numpy(img).pin_memory()      # pinned host memory (e2e source)
+    host_np = host_img.numpy()
+    dev_img = host_img.cuda(non_blocking=True)          # resident copy for the device-timed leg
+    torch.cuda.synchronize()
+
+    def fit_predict(features):
+        model = estim_class_model(features, NB_CLASSES, 'GMM', None, True)
+        return model.predict_proba(features)
+
+    def step_resident():
+        return pipelines.segment_resident(dev_img, fit_predict, FEATURES, SP_SIZE, SP_REGUL, GC_REGUL, 'model')
+
+    def step_e2e():
+        return pipelines.pipe_color2d_slic_features_model_graphcut(host_np, NB_CLASSES, FEATURES, sp_size=SP_SIZE, sp_regul=SP_REGUL,
+                                                                   gc_regul=GC_REGUL, gc_edge_type='model')
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            out = fn()
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device='cuda', dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+        step_e2e()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.isb_profile_enable(1)
+    n0 = lib.isb_launch_count()
+    ms_res, _ = timed(step_resident, args.steps)
+    launches = lib.isb_launch_count() - n0
+    nstage = lib.isb_profile_stage_count()
+    ms_arr, cnt_arr = (C.c_double * nstage)(), (C.c_longlong * nstage)()
+    lib.isb_profile_collect(ms_arr, cnt_arr)
+    lib.isb_profile_enable(0)
+    ms_e2e, (segm, soft) = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    stages = {lib.isb_profile_stage_name(i).decode(): {'ms_per_step': ms_arr[i] / args.steps, 'launches_per_step': cnt_arr[i] / args.steps}
+              for i in range(nstage)}
+    mpix = H * W / 1e6
+    value = world * args.steps * mpix / (ms_res / 1e3)
+    e2e = world * args.steps * mpix / (ms_e2e / 1e3)
+    peak, peak_src = load_peaks()
+    a = stages['slic_assign']
+    t_assign = a['ms_per_step'] / max(a['launches_per_step'], 1) / 1e3
+    achieved = ASSIGN_BYTES_PER_PX * H * W / t_assign / 1e9 if t_assign > 0 else 0.0
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'MPix/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms_res / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'images_per_step_per_gpu': 1, 'sp_size': SP_SIZE, 'sp_regul': SP_REGUL,
+                   'nb_classes': NB_CLASSES, 'gc_regul': GC_REGUL, 'parallelism': 'images sharded over %d GPU(s)' % world,
+                   'l2': 'no explicit flush: per-step working set (f64 image 100 MB + Lab 100 MB + soft output 100 MB) exceeds the 126 MB L2',
+                   'class_model': 'scikit-learn GaussianMixture on the host between the two device phases (as in the reference)'},
+        'e2e': {'value': e2e, 'unit': 'MPix/s', 'ms_per_step': ms_e2e / args.steps, 'h2d_bytes_per_step': int(host_np.nbytes),
+                'd2h_bytes_per_step': int(segm.nbytes + soft.nbytes)},
+        'gpu_launches': int(launches),
+        'roofline': {'kernel': 'k_assign (slic_assign)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                     'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_launch': ASSIGN_BYTES_PER_PX * H * W, 'launch_ms': t_assign * 1e3},
+        'stages': stages,
+        'clocks': clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt, _ = cpu_reference_throughput(args.cpu_images, 1)
+        line['cpu_baseline'] = {'value': v, 'unit': 'MPix/s', 'cores': 1, 'kind': 'port',
+                                'sample': '%d image(s) of 2048x2048, single thread (the reference is single-threaded per image), %.1f s' % (args.cpu_images, dt),
+                                'host_cpus': os.cpu_count()}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cpu-images', type=int, default=4, help='images in the bounded cpu_baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -35,6 +35,13 @@ const char* isb_last_error(void);
 int isb_abi_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long long isb_launch_count(void);
+/* per-stage device timers: CUDA events recorded on the launching stream around each stage's kernels while enabled.
+ * isb_profile_collect() synchronises the recorded events and returns, per stage id, the summed milliseconds and
+ * the number of timed launches (arrays of isb_profile_stage_count() entries); it clears the record list. */
+int isb_profile_enable(int on);
+int isb_profile_stage_count(void);
+const char* isb_profile_stage_name(int id);
+int isb_profile_collect(double* ms_out /* host */, long long* count_out /* host */);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * (i) SLIC -- replaces skimage.segmentation.slic as called from imsegm/superpixels.py:61-63
@@ -46,10 +53,11 @@ long long isb_launch_count(void);
  *   img        : [H,W,C] interleaved, C in {1,3} (gray is replicated, superpixels.py:50-51), dtype = isb_dtype
  *   w_half     : HOST pointer, radius+1 doubles, w_half[0] = centre tap (radius <= 8; radius 0 = no blur)
  *   lab_planar : out, [3,H,W] f64
- *   minmax_out : out, 2 doubles (device) -- min and max of the raw image; max == min makes the result NaN
+ *   minmax_out : out, 4 doubles (device) -- [0] min and [1] max of the raw image ([2..3] scratch); max == min makes
+ *                the result NaN
  *   rescale    : 1 = apply the reference wrapper's min-max rescale when (min != 0 or max != 1); 0 = never */
 int isb_slic_prepare(const void* img, int dtype, int H, int W, int C, const double* w_half, int radius, double ratio,
-                     int rescale, double* lab_planar, double* minmax_out, isb_stream_t stream);
+                     int rescale, double* lab_planar, double* minmax_out /* room for 4 doubles */, isb_stream_t stream);
 
 size_t isb_slic_kmeans_workspace_bytes(int H, int W, int n_seeds, int step_y, int step_x);
 
@@ -100,11 +108,12 @@ int isb_adjacency_edges(const int32_t* seg, int H, int W, int nb, int32_t* edges
 /* compute_unary_cost (imsegm/graph_cuts.py:523-540), compute_edge_weights / compute_edge_model / compute_spatial_dist
  * (:574-657, :383-439, :303-336), create_pairwise_matrix_uniform (:442-456), and pyGCO's float->int conversion.
  *   proba [N,K] f64, edges [E,2] i32 (n_edges read from device n_edges_dev when non-null, else E), centres [N,2] f64
- *   edge_mode: 0 = ones, 1 = model_lT, 2 = model_l1, 3 = model_l2, 4 = spatial only; modes 1..4 divide by the
- *              relative centroid distance
+ *   metric : 0 = constant 1, 1 = lT (max_k dp^2), 2 = l1, 3 = l2   -> w = exp(-d / (2 std(d)^2))
+ *   spatial: 1 = divide by the relative centroid distance (the reference does so for edge_type 'model' and
+ *            'spatial' exactly, not for 'model_l1' / 'model_l2', graph_cuts.py:646)
  *   out: unary [N,K] f64, edge_w [E] f64, and the integerised (unary_i [N,K], edge_wi [E], smooth_i [K,K]) i32 */
 int isb_gc_energies(const double* proba, int N, int K, const int32_t* edges, int E, const int32_t* n_edges_dev,
-                    const double* centres, int edge_mode, double edge_cost, const double* pairwise /* [K,K] device */,
+                    const double* centres, int metric, int spatial, double edge_cost, const double* pairwise /* [K,K] device */,
                     double* unary, double* edge_w, int32_t* unary_i, int32_t* edge_wi, int32_t* smooth_i, void* ws,
                     size_t ws_bytes, isb_stream_t stream);
 size_t isb_gc_energies_workspace_bytes(int N, int K, int E);

@@ -22,6 +22,10 @@ SIGNATURES = {
     'isb_last_error': (C.c_char_p, []),
     'isb_abi_version': (_i, []),
     'isb_launch_count': (_ll, []),
+    'isb_profile_enable': (_i, [_i]),
+    'isb_profile_stage_count': (_i, []),
+    'isb_profile_stage_name': (C.c_char_p, [_i]),
+    'isb_profile_collect': (_i, [C.POINTER(_d), C.POINTER(_ll)]),
     'isb_slic_prepare': (_i, [_vp, _i, _i, _i, _i, C.POINTER(_d), _i, _d, _i, _vp, _vp, _vp]),
     'isb_slic_kmeans_workspace_bytes': (_sz, [_i, _i, _i, _i, _i]),
     'isb_slic_kmeans': (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _i, _i, _vp, _vp, _vp, _sz, _vp]),
@@ -32,7 +36,7 @@ SIGNATURES = {
     'isb_adjacency_workspace_bytes': (_sz, [_i, _i]),
     'isb_adjacency_edges': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     'isb_gc_energies_workspace_bytes': (_sz, [_i, _i, _i]),
-    'isb_gc_energies': (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'isb_gc_energies': (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'isb_alpha_expansion_workspace_bytes': (_sz, [_i, _i, _i]),
     'isb_alpha_expansion': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     'isb_gather': (_i, [_vp, _ll, _vp, _vp, _i, _vp, _vp, _vp]),

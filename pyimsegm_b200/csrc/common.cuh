@@ -8,6 +8,19 @@
 void isb_set_error(const char* fmt, ...);
 extern long long g_isb_launches;
 
+// stage timers (capi.cu): no-ops unless isb_profile_enable(1)
+enum {
+    ISB_PROF_PREPARE = 0, ISB_PROF_ASSIGN, ISB_PROF_UPDATE, ISB_PROF_FINALIZE, ISB_PROF_CONN, ISB_PROF_STATS, ISB_PROF_ADJ,
+    ISB_PROF_ENERGY, ISB_PROF_GC, ISB_PROF_GATHER, ISB_PROF_COUNT
+};
+int isb_prof_begin(int id, cudaStream_t st);
+void isb_prof_end(int handle, cudaStream_t st);
+struct ProfScope {
+    int h; cudaStream_t st;
+    ProfScope(int id, cudaStream_t s) : h(isb_prof_begin(id, s)), st(s) {}
+    ~ProfScope() { if (h >= 0) isb_prof_end(h, st); }
+};
+
 #define ISB_CUDA_CHECK(call)                                                                      \
     do {                                                                                          \
         cudaError_t e__ = (call);                                                                 \

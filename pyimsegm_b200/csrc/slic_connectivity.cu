@@ -343,6 +343,7 @@ extern "C" int isb_enforce_connectivity(const int32_t* labels, int H, int W, int
     size_t need = carve(w, ws, ws_bytes, H, W);
     ISB_REQUIRE(need <= ws_bytes, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ISB_PROF_CONN, st);
     const int n = H * W;
     const int nb = (n + 255) / 256;
     ISB_CUDA_CHECK(cudaMemsetAsync(w.size, 0, sizeof(int) * (size_t)n, st));

@@ -342,11 +342,11 @@ extern "C" int isb_slic_kmeans(const double* lab_planar, int H, int W, const dou
     ISB_LAUNCH_CHECK();
     dim3 agrid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE);
     for (int it = 0; it < max_iter; ++it) {
-        k_assign<<<agrid, 256, 0, st>>>(s, lab_planar, labels);
+        { ProfScope p(ISB_PROF_ASSIGN, st); k_assign<<<agrid, 256, 0, st>>>(s, lab_planar, labels); }
         ISB_LAUNCH_CHECK();
-        k_update<<<(n_seeds + 7) / 8, 256, 0, st>>>(s, lab_planar, labels);
+        { ProfScope p(ISB_PROF_UPDATE, st); k_update<<<(n_seeds + 7) / 8, 256, 0, st>>>(s, lab_planar, labels); }
         ISB_LAUNCH_CHECK();
-        k_finalize_bin<<<1, 1024, 0, st>>>(s, seeds_yx, 0);
+        { ProfScope p(ISB_PROF_FINALIZE, st); k_finalize_bin<<<1, 1024, 0, st>>>(s, seeds_yx, 0); }
         ISB_LAUNCH_CHECK();
     }
     if (centroids) {

@@ -208,6 +208,7 @@ extern "C" int isb_slic_prepare(const void* img, int dtype, int H, int W, int C,
     cudaStream_t st = (cudaStream_t)stream;
     // the two ordered-uint64 accumulators live in the tail of minmax_out's own allocation? no: keep them separate,
     // minmax_out must have room for 4 doubles: [min, max, scratch, scratch]
+    ProfScope prof(ISB_PROF_PREPARE, st);
     unsigned long long* mm = (unsigned long long*)(minmax_out + 2);
     ISB_CUDA_CHECK(cudaMemsetAsync(mm, 0xFF, sizeof(unsigned long long), st));
     ISB_CUDA_CHECK(cudaMemsetAsync(mm + 1, 0x00, sizeof(unsigned long long), st));

@@ -1,0 +1,239 @@
+"""
+Device-resident driver of the SLIC -> descriptors -> GraphCut hot path.
+
+Everything here is plumbing: torch tensors are used purely as device-memory containers and every computation is
+a call into ``libimsegm_b200.so`` through the C-ABI (``include/imsegm_b200.h``).  No torch op touches the data
+path.  The numpy-facing modules (``superpixels``, ``descriptors``, ``graph_cuts``, ``pipelines``) are thin
+wrappers over this class.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+FLAG_BITS = {'mean': 1, 'std': 2, 'energy': 4}
+#: edge_type -> (metric, spatial) of isb_gc_energies; only 'model' and 'spatial' are spatially normalised
+#: (reference graph_cuts.py:646)
+EDGE_MODES = {'': (0, 0), 'model': (1, 1), 'model_lT': (1, 0), 'model_l1': (2, 0), 'model_l2': (3, 0), 'spatial': (0, 1)}
+
+
+def gaussian_half_kernel(sigma, truncate=4.0):
+    """half of scipy.ndimage's normalised 1-D Gaussian: [w0, w1 .. wr], radius r = int(truncate * sigma + 0.5)"""
+    radius = int(truncate * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    phi = phi / phi.sum()
+    return np.ascontiguousarray(phi[radius:], dtype=np.float64), radius
+
+
+def regular_grid_steps(shape, n_points):
+    """(start, step) per axis of skimage.util.regular_grid for an array of ``shape`` and ``n_points`` seeds"""
+    shape = np.asarray(shape)
+    ndim = len(shape)
+    rank = np.argsort(np.argsort(shape))
+    dims = np.sort(shape)
+    space = float(np.prod(shape))
+    if space <= n_points:
+        return [(0, 1)] * ndim
+    steps = np.full(ndim, (space / n_points) ** (1.0 / ndim))
+    if (dims < steps).any():
+        for d in range(ndim):
+            steps[d] = dims[d]
+            space = float(np.prod(dims[d + 1:]))
+            steps[d + 1:] = (space / n_points) ** (1.0 / (ndim - d - 1))
+            if (dims >= steps).all():
+                break
+    starts = (steps // 2).astype(int)
+    steps = np.round(steps).astype(int)
+    pairs = [(int(a), int(b)) for a, b in zip(starts, steps)]
+    return [pairs[i] for i in rank]
+
+
+def slic_seed_grid(H, W, n_segments):
+    (_, _), (sy, ty), (sx, tx) = regular_grid_steps((1, H, W), n_segments)
+    gy, gx = np.meshgrid(np.arange(sy, H, ty), np.arange(sx, W, tx), indexing='ij')
+    seeds = np.stack([gy.ravel(), gx.ravel()], axis=1).astype(np.float64)
+    return np.ascontiguousarray(seeds), int(ty), int(tx)
+
+
+class Engine(object):
+    """owns the device buffers for one image shape at a time and sequences the C-ABI calls on the current stream"""
+
+    def __init__(self, device=None):
+        self.torch = _lib.require_cuda()
+        self.lib = _lib.lib()
+        self.device = self.torch.device('cuda', self.torch.cuda.current_device() if device is None else device)
+        self._bufs = {}
+        self._pinned = {}
+
+    # -- memory helpers ------------------------------------------------------------------------------------------
+    def buf(self, name, shape, dtype):
+        """cached device buffer (grown on demand, never shrunk)"""
+        torch = self.torch
+        shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        n = int(np.prod(shape)) if shape else 1
+        cur = self._bufs.get(name)
+        if cur is None or cur.dtype != dtype or cur.numel() < n:
+            cur = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._bufs[name] = cur
+        return cur[:n].view(shape)
+
+    def to_device(self, arr, name=None):
+        """host ndarray -> device tensor through the current stream (pinned sources copy asynchronously)"""
+        torch = self.torch
+        arr = np.ascontiguousarray(arr)
+        src = torch.from_numpy(arr)
+        if name is None:
+            return src.to(self.device, non_blocking=True)
+        dst = self.buf(name, arr.shape, src.dtype)
+        dst.copy_(src, non_blocking=True)
+        return dst
+
+    def pinned_empty(self, shape, dtype):
+        """pinned host tensor (torch's caching host allocator recycles the blocks once the result is dropped)"""
+        return self.torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+
+    def to_host(self, t, sync=True):
+        out = self.pinned_empty(t.shape, t.dtype)
+        out.copy_(t, non_blocking=True)
+        if sync:
+            self.torch.cuda.current_stream().synchronize()
+        return out.numpy()
+
+    def _ck(self, rc):
+        _lib.check(rc)
+
+    # -- (i) SLIC -------------------------------------------------------------------------------------------------
+    def slic(self, d_img, n_segments, compactness, sigma=1.0, max_iter=10, enforce_connectivity=True,
+             min_size_factor=0.5, max_size_factor=3, slic_zero=False, rescale=True):
+        """device SLIC on a [H,W,C] device tensor; returns (labels int32 [H,W] device, n_labels device int32[1] or None)"""
+        torch, lib = self.torch, self.lib
+        H, W = int(d_img.shape[0]), int(d_img.shape[1])
+        Cn = 1 if d_img.dim() == 2 else int(d_img.shape[2])
+        code = _lib.DTYPE_CODES[str(d_img.dtype).replace('torch.', '')]
+        st = _lib.stream_ptr()
+        lab = self.buf('lab', (3, H, W), torch.float64)
+        mm = self.buf('minmax', (4,), torch.float64)
+        if sigma > 0:
+            w_half, radius = gaussian_half_kernel(sigma)
+        else:
+            w_half, radius = np.ones(1), 0
+        self._ck(lib.isb_slic_prepare(_lib.ptr(d_img), code, H, W, Cn, w_half.ctypes.data_as(C.POINTER(C.c_double)), radius,
+                                      C.c_double(1.0 / compactness), int(bool(rescale)), _lib.ptr(lab), _lib.ptr(mm), st))
+        seeds, ty, tx = slic_seed_grid(H, W, n_segments)
+        n_seeds = len(seeds)
+        step = float(max(1, ty, tx))
+        d_seeds = self.to_device(seeds, 'seeds')
+        wsb = lib.isb_slic_kmeans_workspace_bytes(H, W, n_seeds, ty, tx)
+        ws = self.buf('ws_kmeans', (wsb,), torch.uint8)
+        km = self.buf('labels_km', (H, W), torch.int32)
+        self._ck(lib.isb_slic_kmeans(_lib.ptr(lab), H, W, _lib.ptr(d_seeds), n_seeds, ty, tx, C.c_double(step), int(max_iter),
+                                     int(bool(slic_zero)), _lib.ptr(km), None, _lib.ptr(ws), C.c_size_t(wsb), st))
+        if not enforce_connectivity:
+            return km, None
+        segment_size = 1 * H * W / n_segments
+        min_size, max_size = int(min_size_factor * segment_size), int(max_size_factor * segment_size)
+        cwsb = lib.isb_connectivity_workspace_bytes(H, W)
+        cws = self.buf('ws_conn', (cwsb,), torch.uint8)
+        out = self.buf('labels', (H, W), torch.int32)
+        n_labels = self.buf('n_labels', (1,), torch.int32)
+        self._ck(lib.isb_enforce_connectivity(_lib.ptr(km), H, W, min_size, max_size, _lib.ptr(out), _lib.ptr(n_labels),
+                                              _lib.ptr(cws), C.c_size_t(cwsb), st))
+        return out, n_labels
+
+    def slic_label_bound(self, H, W, n_segments, min_size_factor=0.5):
+        """upper bound on the number of labels after connectivity enforcement (each kept label has >= min_size px)"""
+        min_size = max(1, int(min_size_factor * (H * W / n_segments)))
+        return H * W // min_size + 1
+
+    # -- (ii) descriptors -----------------------------------------------------------------------------------------
+    def segment_stats(self, d_img, d_seg, nb, flags, feat=None, col0=0, want_centres=False, want_counts=False):
+        """colour statistics (+centroids) of a [H,W,3] device image over labels [H,W] int32 in [0, nb)"""
+        torch, lib = self.torch, self.lib
+        H, W = int(d_seg.shape[0]), int(d_seg.shape[1])
+        code = 0 if d_img is None else _lib.DTYPE_CODES[str(d_img.dtype).replace('torch.', '')]
+        bits = 0
+        for f in flags:
+            bits |= FLAG_BITS[f]
+        ncol = 3 * bin(bits).count('1')
+        if feat is None and ncol:
+            feat = self.buf('feat', (nb, ncol), torch.float64)
+        ld = int(feat.shape[1]) if feat is not None else 0
+        centres = self.buf('centres', (nb, 2), torch.float64) if want_centres else None
+        counts = self.buf('counts', (nb,), torch.int32) if want_counts else None
+        wsb = lib.isb_segment_stats_workspace_bytes(nb)
+        ws = self.buf('ws_stats', (wsb,), torch.uint8)
+        self._ck(lib.isb_segment_stats_2d(_lib.ptr(d_img), code, _lib.ptr(d_seg), H, W, int(nb), bits, _lib.ptr(feat), ld, int(col0),
+                                          _lib.ptr(centres), _lib.ptr(counts), _lib.ptr(ws), C.c_size_t(wsb), _lib.stream_ptr()))
+        return feat, centres, counts
+
+    # -- (iii) graph, energies, alpha-expansion ---------------------------------------------------------------------
+    def adjacency(self, d_seg, nb, cap=None):
+        """unique 4-connected label pairs; returns (edges int32 [cap,2] device, n_edges device int32[1], cap)"""
+        torch, lib = self.torch, self.lib
+        H, W = int(d_seg.shape[0]), int(d_seg.shape[1])
+        if cap is None:
+            cap = max(64, 8 * int(nb))
+        wsb = lib.isb_adjacency_workspace_bytes(int(nb), int(cap))
+        ws = self.buf('ws_adj', (wsb,), torch.uint8)
+        edges = self.buf('edges', (cap, 2), torch.int32)
+        n_edges = self.buf('n_edges', (1,), torch.int32)
+        self._ck(lib.isb_adjacency_edges(_lib.ptr(d_seg), H, W, int(nb), _lib.ptr(edges), int(cap), _lib.ptr(n_edges), _lib.ptr(ws),
+                                         C.c_size_t(wsb), _lib.stream_ptr()))
+        return edges, n_edges, cap
+
+    def gc_energies(self, d_proba, d_edges, E, d_n_edges, d_centres, edge_mode, edge_cost, pairwise):
+        torch, lib = self.torch, self.lib
+        N, K = int(d_proba.shape[0]), int(d_proba.shape[1])
+        d_pw = self.to_device(np.ascontiguousarray(pairwise, dtype=np.float64), 'pairwise')
+        unary = self.buf('unary', (N, K), torch.float64)
+        edge_w = self.buf('edge_w', (max(E, 1),), torch.float64)
+        unary_i = self.buf('unary_i', (N, K), torch.int32)
+        edge_wi = self.buf('edge_wi', (max(E, 1),), torch.int32)
+        smooth_i = self.buf('smooth_i', (K, K), torch.int32)
+        wsb = lib.isb_gc_energies_workspace_bytes(N, K, int(E))
+        ws = self.buf('ws_energy', (wsb,), torch.uint8)
+        self._ck(lib.isb_gc_energies(_lib.ptr(d_proba), N, K, _lib.ptr(d_edges), int(E), _lib.ptr(d_n_edges), _lib.ptr(d_centres),
+                                     int(edge_mode[0]), int(edge_mode[1]), C.c_double(edge_cost), _lib.ptr(d_pw), _lib.ptr(unary), _lib.ptr(edge_w),
+                                     _lib.ptr(unary_i), _lib.ptr(edge_wi), _lib.ptr(smooth_i), _lib.ptr(ws), C.c_size_t(wsb),
+                                     _lib.stream_ptr()))
+        return unary, edge_w, unary_i, edge_wi, smooth_i
+
+    def alpha_expansion(self, N, K, E, d_n_edges, d_edges, edge_wi, unary_i, smooth_i, n_iter=-1, init_labels=None):
+        torch, lib = self.torch, self.lib
+        labels = self.buf('gc_labels', (N,), torch.int32)
+        if init_labels is None:
+            labels.zero_()
+        else:
+            labels.copy_(init_labels)
+        energy = self.buf('gc_energy', (1,), torch.int64)
+        stats = self.buf('gc_stats', (4,), torch.int32)
+        wsb = lib.isb_alpha_expansion_workspace_bytes(int(N), int(K), int(E))
+        ws = self.buf('ws_gc', (wsb,), torch.uint8)
+        self._ck(lib.isb_alpha_expansion(int(N), int(K), int(E), _lib.ptr(d_n_edges), _lib.ptr(d_edges), _lib.ptr(edge_wi),
+                                         _lib.ptr(unary_i), _lib.ptr(smooth_i), int(n_iter), _lib.ptr(labels), _lib.ptr(energy),
+                                         _lib.ptr(stats), _lib.ptr(ws), C.c_size_t(wsb), _lib.stream_ptr()))
+        return labels, energy, stats
+
+    def gather(self, d_seg, lut_i=None, lut_p=None):
+        torch, lib = self.torch, self.lib
+        H, W = int(d_seg.shape[0]), int(d_seg.shape[1])
+        out_i = self.buf('segm', (H, W), torch.int32) if lut_i is not None else None
+        K = int(lut_p.shape[1]) if lut_p is not None else 0
+        out_p = self.buf('segm_soft', (H, W, K), torch.float64) if lut_p is not None else None
+        self._ck(lib.isb_gather(_lib.ptr(d_seg), C.c_longlong(H * W), _lib.ptr(lut_i), _lib.ptr(lut_p), K, _lib.ptr(out_i),
+                                _lib.ptr(out_p), _lib.stream_ptr()))
+        return out_i, out_p
+
+
+_ENGINES = {}
+
+
+def get_engine(device=None):
+    """one engine per device (buffers are cached inside)"""
+    torch = _lib.require_cuda()
+    idx = torch.cuda.current_device() if device is None else int(device)
+    if idx not in _ENGINES:
+        _ENGINES[idx] = Engine(idx)
+    return _ENGINES[idx]

@@ -1,0 +1,203 @@
+"""
+Segmentation pipelines: SLIC -> per-superpixel features -> class model -> GraphCut, resident on the GPU.
+
+Mirror of the reference module ``imsegm/pipelines.py`` for the unsupervised hot path (same names, arguments
+and return values):
+
+* :func:`pipe_color2d_slic_features_model_graphcut`     (reference pipelines.py:46-110)
+* :func:`estim_model_classes_group`                     (reference pipelines.py:113-157)
+* :func:`segment_color2d_slic_features_model_graphcut`  (reference pipelines.py:160-241)
+* :func:`compute_color2d_superpixels_features`          (reference pipelines.py:244-270)
+
+The image goes to the device once; label map, features, graph, energies and the cut never leave it.  The only
+host round trip is the class model (scikit-learn, as in the reference): features [N, D] down, probabilities
+[N, K] up.
+"""
+import logging
+
+import numpy as np
+
+from .descriptors import FEATURES_SET_COLOR, compute_selected_features_img2d, flags_are_native
+from .engine import EDGE_MODES, get_engine
+from .graph_cuts import _edge_mode, compute_pairwise_cost, estim_class_model, segment_graph_cut_general
+from .superpixels import _as_rgb_like, _supported_dtype, device_adjacency, slic_params
+
+#: basic features extracted from superpixels (reference pipelines.py:35)
+FTS_SET_SIMPLE = FEATURES_SET_COLOR
+#: default clustering for unsupervised segmentation (reference pipelines.py:39 -> classification.DEFAULT_CLUSTERING)
+CLUSTER_METHOD = 'kMeans'
+#: images left out during cross-validation training (reference pipelines.py:41)
+CROSS_VAL_LEAVE_OUT = 2
+#: default number of workers of the reference's process pool (pipelines.py:43); the GPU path shards images over
+#: devices instead, the value is kept for signature compatibility
+NB_WORKERS = 1
+
+
+class DeviceSuperpixels(object):
+    """device-resident result of SLIC + descriptors for one image"""
+    __slots__ = ('d_img', 'd_seg', 'd_n_labels', 'nb_bound', 'd_feat', 'd_centres', 'shape')
+
+
+def _device_slic_features(eng, image, dict_features, sp_size, sp_regul):
+    """H2D, SLIC, fused colour statistics + centroids; everything stays on the device"""
+    if sp_regul <= 0.:
+        raise ValueError('slic. regularisation must be positive')
+    on_device = hasattr(image, 'is_cuda')
+    if not on_device:
+        image = _supported_dtype(_as_rgb_like(image))
+    H, W = int(image.shape[0]), int(image.shape[1])
+    n_seg, compact = slic_params((H, W), sp_size, sp_regul)
+    if n_seg < 1:
+        raise ValueError('superpixel size %r is larger than the image %r' % (sp_size, tuple(image.shape)))
+    res = DeviceSuperpixels()
+    res.shape = (H, W)
+    res.d_img = image if on_device else eng.to_device(image, 'image')
+    res.d_seg, res.d_n_labels = eng.slic(res.d_img, n_seg, compact, sigma=1.0)
+    res.nb_bound = eng.slic_label_bound(H, W, n_seg)
+    flags = [f for f in ('mean', 'std', 'energy') if f in dict_features.get('color', ())]
+    res.d_feat, res.d_centres, _ = eng.segment_stats(res.d_img, res.d_seg, res.nb_bound, flags, want_centres=True)
+    return res
+
+
+def compute_color2d_superpixels_features(image, dict_features, sp_size=30, sp_regul=0.2):
+    """ segment the image into superpixels and estimate features per superpixel (reference pipelines.py:244-270)
+
+    :return tuple(ndarray,ndarray): superpixel map [H, W], features [N, D]
+    """
+    if sp_regul <= 0.:
+        raise ValueError('slic. regularisation must be positive')
+    image = np.asarray(image)
+    eng = get_engine()
+    if image.ndim == 3 and flags_are_native(dict_features):
+        res = _device_slic_features(eng, image, dict_features, sp_size, sp_regul)
+        nb = int(eng.to_host(res.d_n_labels)[0])
+        slic = eng.to_host(res.d_seg).astype(np.int64)
+        features = eng.to_host(res.d_feat[:nb]).copy()
+    else:
+        if sp_regul <= 0.:
+            raise ValueError('slic. regularisation must be positive')
+        from .superpixels import segment_slic_img2d
+        slic = segment_slic_img2d(image, sp_size=sp_size, relative_compact=sp_regul)
+        features, _ = compute_selected_features_img2d(image, slic, dict_features)
+    features[np.isnan(features)] = 0
+    return slic, features
+
+
+def _device_graphcut(eng, res, nb, proba, gc_regul, gc_edge_type, want_soft=True):
+    """device tail of the pipeline: adjacency, energies, alpha-expansion, LUT gathers"""
+    proba = np.ascontiguousarray(proba, dtype=np.float64)
+    K = proba.shape[1]
+    d_proba = eng.to_device(proba, 'proba')
+    pairwise = compute_pairwise_cost(gc_regul, proba.shape)
+    scalar = not isinstance(gc_regul, (list, np.ndarray))
+    d_soft = None
+    if scalar and gc_regul <= 0:
+        graph_labels = np.argmin(np.abs(-np.log(np.clip(proba, 0.01, 0.99))), axis=-1).astype(np.int32)
+        d_labels = eng.to_device(graph_labels, 'gc_labels_in')
+    else:
+        d_edges, E = device_adjacency(eng, res.d_seg, nb)
+        mode = _edge_mode(gc_edge_type)
+        _, _, unary_i, edge_wi, smooth_i = eng.gc_energies(d_proba, d_edges, E, None, res.d_centres, mode, 1.0, pairwise)
+        d_labels, _, _ = eng.alpha_expansion(nb, K, E, None, d_edges, edge_wi, unary_i, smooth_i, -1)
+    d_segm, d_soft = eng.gather(res.d_seg, d_labels, d_proba if want_soft else None)
+    return d_labels, d_segm, d_soft
+
+
+def _segment_with_proba_fn(image, proba_fn, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type, debug_visual, classes=None):
+    image = np.asarray(image)
+    eng = get_engine()
+    native = image.ndim == 3 and flags_are_native(dict_features) and gc_edge_type not in ('color', 'features')
+    if not native or debug_visual is not None:
+        # general path: every stage still runs on the device, but through the numpy-facing stage functions
+        slic, features = compute_color2d_superpixels_features(image, dict_features, sp_size=sp_size, sp_regul=sp_regul)
+        if debug_visual is not None:
+            img3 = image if image.ndim == 3 else np.stack([image] * 3, axis=-1)
+            debug_visual['image'] = img3
+            debug_visual['slic'] = slic
+            means = np.stack([np.bincount(slic.ravel(), weights=img3[..., c].ravel()) for c in range(3)], 1)
+            debug_visual['slic_mean'] = (means / np.maximum(np.bincount(slic.ravel()), 1)[:, None])[slic]
+        proba = proba_fn(features)
+        segm_soft = proba[slic]
+        graph_labels = segment_graph_cut_general(slic, proba, image, features, gc_regul, gc_edge_type, debug_visual=debug_visual)
+        if classes is not None:
+            graph_labels = classes[graph_labels]
+        return graph_labels[slic], segm_soft
+    res = _device_slic_features(eng, image, dict_features, sp_size, sp_regul)
+    nb = int(eng.to_host(res.d_n_labels)[0])
+    features = eng.to_host(res.d_feat[:nb]).copy()
+    features[np.isnan(features)] = 0
+    proba = proba_fn(features)
+    logging.debug('list of probabilities: %r', proba.shape)
+    d_labels, d_segm, d_soft = _device_graphcut(eng, res, nb, proba, gc_regul, gc_edge_type)
+    torch = eng.torch
+    segm_h = eng.pinned_empty(d_segm.shape, d_segm.dtype)
+    soft_h = eng.pinned_empty(d_soft.shape, d_soft.dtype)
+    segm_h.copy_(d_segm, non_blocking=True)
+    soft_h.copy_(d_soft, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    segm = segm_h.numpy()
+    if classes is not None:
+        segm = np.asarray(classes)[segm]
+    return segm, soft_h.numpy()
+
+
+def segment_resident(d_image, proba_fn, dict_features, sp_size=30, sp_regul=0.2, gc_regul=1., gc_edge_type='model'):
+    """ the same hot path with the image ALREADY on the device (a cuda tensor [H, W, 3]) and the results left
+    there: returns (segm int32 [H, W], segm_soft float64 [H, W, K]) device tensors.  ``proba_fn`` maps the host
+    feature matrix [N, D] to class probabilities [N, K] (fit + predict for the unsupervised pipeline). """
+    eng = get_engine()
+    res = _device_slic_features(eng, d_image, dict_features, sp_size, sp_regul)
+    nb = int(eng.to_host(res.d_n_labels)[0])
+    features = eng.to_host(res.d_feat[:nb]).copy()
+    features[np.isnan(features)] = 0
+    _, d_segm, d_soft = _device_graphcut(eng, res, nb, proba_fn(features), gc_regul, gc_edge_type)
+    return d_segm, d_soft
+
+
+def pipe_color2d_slic_features_model_graphcut(image, nb_classes, dict_features, sp_size=30, sp_regul=0.2, pca_coef=None,
+                                              use_scaler=True, estim_model='GMM', gc_regul=1., gc_edge_type='model',
+                                              debug_visual=None):
+    """ complete pipeline: superpixels, features, class model estimated on this image, GraphCut
+    (reference pipelines.py:46-110)
+
+    :param ndarray image: input RGB image
+    :param int nb_classes: number of classes to be segmented
+    :param dict dict_features: {'color': [...], ...}
+    :return tuple(ndarray,ndarray): segmentation [H, W] int32, soft segmentation [H, W, nb_classes] float64
+    """
+    logging.info('PIPELINE Superpixels-Features-GMM-GraphCut')
+    holder = {}
+
+    def _fit_predict(features):
+        holder['model'] = estim_class_model(features, nb_classes, estim_model, pca_coef, use_scaler)
+        return holder['model'].predict_proba(features)
+
+    return _segment_with_proba_fn(image, _fit_predict, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type, debug_visual)
+
+
+def estim_model_classes_group(list_images, nb_classes, dict_features, sp_size=30, sp_regul=0.2, use_scaler=True,
+                              pca_coef=None, model_type='GMM', nb_workers=NB_WORKERS):
+    """ one class model from the superpixel features of a sequence of images (reference pipelines.py:113-157);
+    the per-image work that the reference spreads over a process pool runs back to back on the GPU
+
+    :return tuple(model, list(ndarray)): fitted sklearn pipeline, list of per-image features
+    """
+    list_features = []
+    for image in list_images:
+        _, features = compute_color2d_superpixels_features(image, dict_features, sp_size=sp_size, sp_regul=sp_regul)
+        list_features.append(features)
+    features = np.nan_to_num(np.concatenate(tuple(list_features), axis=0))
+    model = estim_class_model(features, nb_classes, model_type, pca_coef, use_scaler)
+    return model, list_features
+
+
+def segment_color2d_slic_features_model_graphcut(image, model_pipeline, dict_features, sp_size=30, sp_regul=0.2, gc_regul=1.,
+                                                 gc_edge_type='model', debug_visual=None):
+    """ complete pipeline with a given (already fitted) model (reference pipelines.py:160-241)
+
+    :return tuple(ndarray,ndarray): segmentation [H, W], soft segmentation [H, W, K]
+    """
+    logging.info('PIPELINE Superpixels-Features-Model-GraphCut')
+    classes = getattr(model_pipeline, 'classes_', None)
+    return _segment_with_proba_fn(image, model_pipeline.predict_proba, dict_features, sp_size, sp_regul, gc_regul,
+                                  gc_edge_type, debug_visual, classes=classes)

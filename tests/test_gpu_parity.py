@@ -1,0 +1,178 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from conftest import synth_disc, synth_regions
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def eng():
+    from pyimsegm_b200.engine import get_engine
+    return get_engine()
+
+
+def _slic_both(oracle, img, sp_size, regul):
+    from pyimsegm_b200 import superpixels as sp
+    got = sp.segment_slic_img2d(img, sp_size, regul)
+    want = oracle.segment_slic_img2d(img, sp_size, regul)
+    return got, want
+
+
+@pytest.mark.parametrize('case', ['rand', 'disc', 'flat', 'u8', 'gray', 'odd'])
+def test_slic_label_map_bit_exact(oracle, case):
+    rng = np.random.RandomState(0)
+    if case == 'rand':
+        img = rng.random_sample((125, 150, 3)) / 2.
+        img[:, :75] += 0.5
+        args = (20, 0.2)
+    elif case == 'disc':
+        img, args = synth_disc(256, 256), (25, 0.2)
+    elif case == 'flat':
+        img, args = synth_disc(200, 240, noise=0.0), (16, 0.3)
+    elif case == 'u8':
+        img, args = (synth_disc(256, 256) * 255).astype(np.uint8), (30, 0.3)
+    elif case == 'gray':
+        img, args = synth_disc(128, 160)[..., 0], (20, 0.2)
+    else:
+        img, args = synth_regions(203, 317, seed=5)[0], (17, 0.25)
+    got, want = _slic_both(oracle, img, *args)
+    assert got.dtype == np.int64 and got.shape == img.shape[:2]
+    assert np.array_equal(got, want)
+    assert set(np.unique(got)) == set(range(got.max() + 1))
+
+
+def test_color_stats_match_oracle_and_reference_module(oracle):
+    from pyimsegm_b200 import descriptors as ds
+    img, _ = synth_regions(300, 400, seed=3)
+    seg = oracle.segment_slic_img2d(img, 20, 0.2)
+    for im in (img, (img * 255).astype(np.uint8), img.astype(np.float32)):
+        for name, fn_o in (('mean', oracle.color2d_mean), ('energy', oracle.color2d_energy), ('std', oracle.color2d_std)):
+            got = getattr(ds, 'cython_img2d_color_%s' % name)(im, seg)
+            np.testing.assert_allclose(got, fn_o(im, seg), rtol=1e-6, atol=1e-9)
+    fc = oracle.ref_features_cython()
+    if fc is not None:
+        ref = np.array(fc.computeColorImage2dEnergy(img.astype(np.float32), seg.astype(np.int32)))
+        np.testing.assert_allclose(ds.cython_img2d_color_energy(img, seg), ref, rtol=1e-6, atol=1e-9)
+    fts, names = ds.compute_image2d_color_statistic(img, seg, ('mean', 'std', 'energy', 'meanGrad'))
+    want = oracle.image2d_color_statistic(img, seg, ('mean', 'std', 'energy', 'meanGrad'))
+    assert fts.shape == (seg.max() + 1, 12) and len(names) == 12
+    np.testing.assert_allclose(fts, want, rtol=1e-6, atol=1e-9)
+
+
+def test_reference_doctest_goldens_descriptors():
+    """imsegm/descriptors.py:218-283 and :796-813"""
+    from pyimsegm_b200 import descriptors as ds
+    image = np.zeros((2, 10, 3))
+    image[:, 2:6, 0] = 1
+    image[:, 3:7, 1] = 3
+    image[:, 4:9, 2] = 2
+    segm = np.array([[0] * 5 + [1] * 5] * 2)
+    np.testing.assert_allclose(ds.cython_img2d_color_mean(image, segm), [[0.6, 1.2, 0.4], [0.2, 1.2, 1.6]], rtol=1e-12)
+    np.testing.assert_allclose(ds.cython_img2d_color_energy(image, segm), [[0.6, 3.6, 0.8], [0.2, 3.6, 3.2]], rtol=1e-12)
+    np.testing.assert_allclose(ds.cython_img2d_color_std(image, segm),
+                               [[0.48989794, 1.46969383, 0.80000003], [0.40000001, 1.46969383, 0.80000001]], rtol=1e-7)
+    features, names = ds.compute_image2d_color_statistic(image, segm)
+    assert names[:3] == ['color-ch1_mean', 'color-ch2_mean', 'color-ch3_mean'] and features.shape == (2, 15)
+    want = [[0.6, 1.2, 0.4, 0.5, 1.5, 0.8, 0.6, 3.6, 0.8, 1.0, 0.0, 0.0, 0.2, 0.6, 0.4],
+            [0.2, 1.2, 1.6, 0.4, 1.5, 0.8, 0.2, 3.6, 3.2, 0.0, 0.0, 2.0, -0.2, -0.6, -0.6]]
+    assert np.round(features, 1).tolist() == want
+
+
+def test_reference_doctest_goldens_graph():
+    """imsegm/superpixels.py:163-168, :211-215; imsegm/graph_cuts.py:587-609, :687-716"""
+    from pyimsegm_b200 import graph_cuts as gc
+    from pyimsegm_b200 import superpixels as sp
+    grid = np.array([[0] * 5 + [1] * 5, [2] * 5 + [3] * 5])
+    v, edges = sp.make_graph_segm_connect_grid2d_conn4(grid)
+    assert v.tolist() == [0, 1, 2, 3] and [list(map(int, e)) for e in edges] == [[0, 1], [0, 2], [1, 3], [2, 3]]
+    segm = np.array([[0] * 6 + [1] * 5, [0] * 6 + [2] * 5])
+    assert sp.superpixel_centers(segm) == [(0.5, 2.5), (0.0, 8.0), (1.0, 8.0)]
+    segments = np.array([[0] * 3 + [1] * 5 + [2] * 4, [4] * 4 + [5] * 5 + [6] * 3])
+    np.random.seed(0)
+    _ = np.random.random(segments.shape + (3,)) * 255
+    features = np.random.random((segments.max() + 1, 15)) * 10
+    proba = np.random.random((segments.max() + 1, 2))
+    edges, weights = gc.compute_edge_weights(segments)
+    assert edges.tolist() == [[0, 1], [1, 2], [0, 4], [1, 4], [1, 5], [2, 5], [4, 5], [2, 6], [5, 6]]
+    assert np.round(weights, 2).tolist() == [1.0] * 9
+    _, weights = gc.compute_edge_weights(segments, edge_type='spatial')
+    assert np.round(weights, 3).tolist() == [0.776, 0.69, 2.776, 0.853, 2.194, 0.853, 0.69, 2.776, 0.776]
+    _, weights = gc.compute_edge_weights(segments, features=features, edge_type='features')
+    assert np.round(weights, 3).tolist() == [0.031, 0.005, 0.051, 0.032, 0.096, 0.013, 0.018, 0.033, 0.013]
+    _, weights = gc.compute_edge_weights(segments, proba=proba, edge_type='model')
+    assert np.round(weights, 3).tolist() == [0.001, 0.028, 1.122, 0.038, 0.117, 0.688, 0.487, 1.152, 0.282]
+    # graph cut goldens
+    np.random.seed(0)
+    segments = np.array([[0] * 3 + [2] * 3 + [4] * 3 + [6] * 3 + [8] * 3, [1] * 3 + [3] * 3 + [5] * 3 + [7] * 3 + [9] * 3])
+    proba = np.array([[0.1] * 6 + [0.9] * 4, [0.9] * 6 + [0.1] * 4], dtype=float).T
+    proba += (0.5 - np.random.random(proba.shape)) * 0.2
+    labels = gc.segment_graph_cut_general(segments, proba, gc_regul=0., edge_type='')
+    assert labels.tolist() == [1, 1, 1, 1, 1, 1, 0, 0, 0, 0]
+    labels = gc.segment_graph_cut_general(segments, proba, gc_regul=1., edge_type='spatial')
+    assert labels.dtype == np.int32
+    assert labels[segments].tolist() == [[1] * 9 + [0] * 6] * 2
+
+
+def _random_graph_problem(rng, n, k, deg=3.0, strong=True):
+    m = int(n * deg)
+    a = rng.randint(0, n, m)
+    b = rng.randint(0, n, m)
+    keep = a != b
+    pairs = np.unique(np.stack([np.minimum(a, b)[keep], np.maximum(a, b)[keep]], 1), axis=0)
+    w = rng.random_sample(len(pairs)) * 2 + 1e-3
+    p = rng.dirichlet(np.ones(k) * (0.3 if strong else 2.0), n)
+    return pairs.astype(np.int32), w, p
+
+
+@pytest.mark.parametrize('n,k,regul', [(12, 2, 1.0), (300, 3, 0.8), (2000, 4, 2.0), (7000, 3, 1.5), (9000, 5, 3.0)])
+def test_alpha_expansion_labels_bit_exact(oracle, n, k, regul):
+    from pyimsegm_b200 import graph_cuts as gc
+    rng = np.random.RandomState(n + k)
+    edges, w, p = _random_graph_problem(rng, n, k)
+    unary = gc.compute_unary_cost(p)
+    pw = gc.compute_pairwise_cost(regul, p.shape)
+    want, e_want, _ = oracle.cut_general_graph(edges, w, unary, pw, n_iter=-1, return_energy=True)
+    got = gc.cut_general_graph(edges, w, unary, pw, n_iter=-1)
+    assert got.dtype == np.int32
+    assert np.array_equal(got, want)
+    got2 = gc.cut_general_graph(edges, w, unary, pw, n_iter=999)
+    want2 = oracle.cut_general_graph(edges, w, unary, pw, n_iter=999)
+    assert np.array_equal(got2, want2)
+
+
+def test_energies_match_oracle(oracle):
+    from pyimsegm_b200 import graph_cuts as gc
+    img, _ = synth_regions(256, 320, seed=4)
+    seg = oracle.segment_slic_img2d(img, 16, 0.2)
+    rng = np.random.RandomState(1)
+    proba = rng.dirichlet(np.ones(3), seg.max() + 1)
+    for et in ('model', 'model_l1', 'model_l2', 'spatial', ''):
+        e_g, w_g = gc.compute_edge_weights(seg, proba=proba, edge_type=et)
+        e_o, w_o = oracle.edge_weights(seg, proba, et)
+        assert np.array_equal(e_g, e_o)
+        np.testing.assert_allclose(w_g, w_o, rtol=1e-9)
+    labels = gc.segment_graph_cut_general(seg, proba, gc_regul=2., edge_type='model')
+    want = oracle.segment_graph_cut_general(seg, proba, 2., 'model')
+    assert np.array_equal(labels, want)
+
+
+def test_pipeline_with_shared_model_equals_oracle(oracle):
+    """entry point 3.2 (imsegm/pipelines.py:160): same fitted model on both sides, label maps must be identical"""
+    from sklearn import mixture, pipeline, preprocessing
+    from pyimsegm_b200 import pipelines as pl
+    img, _ = synth_regions(384, 512, seed=7)
+    feats = {'color': ['mean']}
+    slic_o, fts_o = oracle.compute_color2d_superpixels_features(img, ('mean',), 24, 0.2)
+    model = pipeline.Pipeline([('std_scaler', preprocessing.StandardScaler()),
+                               ('model', mixture.GaussianMixture(3, covariance_type='full', random_state=0))]).fit(fts_o)
+    segm, soft = pl.segment_color2d_slic_features_model_graphcut(img, model, feats, sp_size=24, sp_regul=0.2, gc_regul=1.)
+    segm_o, soft_o, _, _ = oracle.segment_with_model(img, model.predict_proba, ('mean',), 24, 0.2, 1., 'model')
+    assert segm.shape == img.shape[:2] and soft.shape == img.shape[:2] + (3,)
+    assert np.array_equal(segm, segm_o)
+    np.testing.assert_allclose(soft, soft_o, rtol=1e-6, atol=1e-9)
+    # the self-estimating pipeline: shapes + sanity (the GMM is unseeded in the reference, so no label parity)
+    segm2, soft2 = pl.pipe_color2d_slic_features_model_graphcut(img, 3, feats, sp_size=24)
+    assert segm2.shape == img.shape[:2] and soft2.shape == img.shape[:2] + (3,)
+    np.testing.assert_allclose(soft2.sum(-1), 1.0, rtol=1e-9)
