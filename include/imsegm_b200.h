@@ -112,7 +112,8 @@ int isb_adjacency_edges(const int32_t* seg, int H, int W, int nb, int32_t* edges
  *   spatial: 1 = divide by the relative centroid distance (the reference does so for edge_type 'model' and
  *            'spatial' exactly, not for 'model_l1' / 'model_l2', graph_cuts.py:646)
  *   out: unary [N,K] f64, edge_w [E] f64, and the integerised (unary_i [N,K], edge_wi [E], smooth_i [K,K]) i32 */
-int isb_gc_energies(const double* proba, int N, int K, const int32_t* edges, int E, const int32_t* n_edges_dev,
+int isb_gc_energies(const double* proba, int N, const int32_t* n_nodes_dev /* optional device N */, int K, const int32_t* edges, int E,
+                    const int32_t* n_edges_dev,
                     const double* centres, int metric, int spatial, double edge_cost, const double* pairwise /* [K,K] device */,
                     double* unary, double* edge_w, int32_t* unary_i, int32_t* edge_wi, int32_t* smooth_i, void* ws,
                     size_t ws_bytes, isb_stream_t stream);
@@ -123,10 +124,27 @@ size_t isb_gc_energies_workspace_bytes(int N, int K, int E);
  * residual graph (BK's SINK segment) so labels are identical to the oracle's.
  *   labels : in/out [N] i32 (initial labeling, zeros for the reference call);  energy_out : device int64 */
 size_t isb_alpha_expansion_workspace_bytes(int N, int K, int E);
-int isb_alpha_expansion(int N, int K, int E, const int32_t* n_edges_dev, const int32_t* edges, const int32_t* edge_wi,
+int isb_alpha_expansion(int N, const int32_t* n_nodes_dev /* optional device N */, int K, int E, const int32_t* n_edges_dev,
+                        const int32_t* edges, const int32_t* edge_wi,
                         const int32_t* unary_i, const int32_t* smooth_i, int n_iter, int32_t* labels, int64_t* energy_out,
                         int32_t* stats_out /* optional [4]: moves, flows, sweeps, relabels */, void* ws, size_t ws_bytes,
                         isb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * class model -- replaces the host round trip of estim_class_model / predict_proba (imsegm/graph_cuts.py:73-163 default
+ * 'GMM', imsegm/pipelines.py:95-96): StandardScaler + sklearn-style full-covariance GaussianMixture EM, n_init
+ * restarts run concurrently (one CTA each), best lower bound wins.
+ *   feat [N, ld] f64 (first D columns used), n_dev: optional device int32 with the real row count (<= N)
+ *   init_labels: optional [n_init, N] i32 hard assignments (deterministic start); else k-means++/Lloyd from `seed`
+ *   proba: out [N, K];  params_out: optional, isb_gmm_params_len(D, K) doubles:
+ *     scaler mean[D] | scaler scale[D] | weights[K] | means[K,D] | covariances[K,D,D] | precisions_cholesky[K,D,D] |
+ *     lower_bound | n_iter | converged | ok | best_init
+ * ------------------------------------------------------------------------------------------------------------------ */
+size_t isb_gmm_workspace_bytes(int N, int D, int K, int n_init);
+int isb_gmm_params_len(int D, int K);
+int isb_gmm_fit_predict(const double* feat, int N, int D, int ld, const int32_t* n_dev, int K, int n_init, int max_iter, double tol,
+                        double reg_covar, int use_scaler, unsigned long long seed, const int32_t* init_labels, double* proba,
+                        double* params_out, void* ws, size_t ws_bytes, isb_stream_t stream);
 
 /* final LUT gathers of imsegm/pipelines.py:104,109:  segm = graph_labels[slic], segm_soft = proba[slic]
  *   lut_i [nb] i32 (optional), lut_p [nb,K] f64 (optional); outputs [H,W] i32 / [H,W,K] f64 */

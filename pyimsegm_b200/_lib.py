@@ -36,9 +36,12 @@ SIGNATURES = {
     'isb_adjacency_workspace_bytes': (_sz, [_i, _i]),
     'isb_adjacency_edges': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     'isb_gc_energies_workspace_bytes': (_sz, [_i, _i, _i]),
-    'isb_gc_energies': (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'isb_gc_energies': (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'isb_alpha_expansion_workspace_bytes': (_sz, [_i, _i, _i]),
-    'isb_alpha_expansion': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'isb_alpha_expansion': (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'isb_gmm_workspace_bytes': (_sz, [_i, _i, _i, _i]),
+    'isb_gmm_params_len': (_i, [_i, _i]),
+    'isb_gmm_fit_predict': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _d, _d, _i, C.c_ulonglong, _vp, _vp, _vp, _vp, _sz, _vp]),
     'isb_gather': (_i, [_vp, _ll, _vp, _vp, _i, _vp, _vp, _vp]),
 }
 

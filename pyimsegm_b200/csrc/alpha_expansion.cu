@@ -32,7 +32,7 @@ constexpr int KMAX_S = 16; // smooth-cost table cached in smem up to K = 16
 
 struct GcArgs {
     int N, K, E_cap;
-    const int* n_edges_dev;
+    const int* n_edges_dev; const int* n_nodes_dev;
     const int* edges; const int* w; const int* D; const int* V;
     int n_iter;
     int* labels;
@@ -171,17 +171,17 @@ __global__ void __launch_bounds__(NT, 1) k_alpha_expansion(GcArgs a)
     __shared__ int s_stats[4];
 
     Ctx c;
-    c.N = a.N; c.K = a.K;
+    c.N = a.n_nodes_dev ? min(*a.n_nodes_dev, a.N) : a.N; c.K = a.K;
     c.E = a.n_edges_dev ? min(*a.n_edges_dev, a.E_cap) : a.E_cap;
     c.edges = a.edges; c.w = a.w; c.D = a.D; c.V = a.V;
     c.off = a.off; c.adj_v = a.adj_v; c.adj_e = a.adj_e;
     c.s_V = s_V; c.s_red = s_red;
-    const size_t smem_need = sizeof(long long) * 2 * (size_t)a.N + sizeof(int) * (2 * (size_t)c.E + (size_t)a.N);
+    const size_t smem_need = sizeof(long long) * 2 * (size_t)c.N + sizeof(int) * (2 * (size_t)c.E + (size_t)c.N);
     if (smem_need <= (size_t)a.dyn_bytes) {
         // layout: excess[N] ll | tcap[N] ll | flow[E] | cap[E] | height[N]
         long long* p = (long long*)dyn;
-        c.excess = p; c.tcap = p + a.N;
-        int* q = (int*)(p + 2 * (size_t)a.N);
+        c.excess = p; c.tcap = p + c.N;
+        int* q = (int*)(p + 2 * (size_t)c.N);
         c.flow = q; c.cap = q + c.E; c.height = q + 2 * (size_t)c.E;
     } else {
         c.excess = a.g_excess; c.tcap = a.g_tcap; c.flow = a.g_flow; c.cap = a.g_cap; c.height = a.g_height;
@@ -375,7 +375,7 @@ extern "C" size_t isb_alpha_expansion_workspace_bytes(int N, int K, int E)
     return carve_gc(w, nullptr, 0, N, E);
 }
 
-extern "C" int isb_alpha_expansion(int N, int K, int E, const int32_t* n_edges_dev, const int32_t* edges, const int32_t* edge_wi,
+extern "C" int isb_alpha_expansion(int N, const int32_t* n_nodes_dev, int K, int E, const int32_t* n_edges_dev, const int32_t* edges, const int32_t* edge_wi,
                                    const int32_t* unary_i, const int32_t* smooth_i, int n_iter, int32_t* labels, int64_t* energy_out,
                                    int32_t* stats_out, void* ws, size_t ws_bytes, isb_stream_t stream)
 {
@@ -386,7 +386,7 @@ extern "C" int isb_alpha_expansion(int N, int K, int E, const int32_t* n_edges_d
     size_t need = carve_gc(w, ws, ws_bytes, N, E);
     ISB_REQUIRE(need <= ws_bytes, "workspace too small");
     GcArgs a;
-    a.N = N; a.K = K; a.E_cap = E; a.n_edges_dev = n_edges_dev;
+    a.N = N; a.K = K; a.E_cap = E; a.n_edges_dev = n_edges_dev; a.n_nodes_dev = n_nodes_dev;
     a.edges = edges; a.w = edge_wi; a.D = unary_i; a.V = smooth_i; a.n_iter = n_iter;
     a.labels = labels; a.energy_out = (long long*)energy_out; a.stats = stats_out;
     a.off = w.off; a.fill = w.fill; a.adj_v = w.adj_v; a.adj_e = w.adj_e; a.u0 = w.u0; a.u1 = w.u1; a.newlab = w.newlab;

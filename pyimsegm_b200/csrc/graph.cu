@@ -165,7 +165,7 @@ __device__ double block_max(double v, double* s_red)
 }
 
 // single CTA per graph.  vfeat [N, D]: the per-vertex vectors the edge metric compares (proba for 'model').
-__global__ void __launch_bounds__(1024) k_gc_energies(const double* __restrict__ proba, int N, int K, const int* __restrict__ edges, int E_in,
+__global__ void __launch_bounds__(1024) k_gc_energies(const double* __restrict__ proba, int N_in, const int* n_nodes_dev, int K, const int* __restrict__ edges, int E_in,
                                                       const int* n_edges_dev, const double* __restrict__ centres,
                                                       const double* __restrict__ vfeat, int D, int metric, int spatial,
                                                       double edge_cost, const double* __restrict__ pairwise, double* unary,
@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(1024) k_gc_energies(const double* __restrict__
 {
     __shared__ double s_red[32];
     const int E = n_edges_dev ? min(*n_edges_dev, E_in) : E_in;
+    const int N = n_nodes_dev ? min(*n_nodes_dev, N_in) : N_in;
     // unary = |-log(clip(p, 0.01, 0.99))|
     double umax = 0.0;
     for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
@@ -290,7 +291,7 @@ extern "C" int isb_adjacency_edges(const int32_t* seg, int H, int W, int nb, int
 
 extern "C" size_t isb_gc_energies_workspace_bytes(int N, int K, int E) { return isb_align(sizeof(double) * (size_t)(E > 0 ? E : 1)); }
 
-extern "C" int isb_gc_energies(const double* proba, int N, int K, const int32_t* edges, int E, const int32_t* n_edges_dev,
+extern "C" int isb_gc_energies(const double* proba, int N, const int32_t* n_nodes_dev, int K, const int32_t* edges, int E, const int32_t* n_edges_dev,
                                const double* centres, int metric, int spatial, double edge_cost, const double* pairwise, double* unary,
                                double* edge_w, int32_t* unary_i, int32_t* edge_wi, int32_t* smooth_i, void* ws, size_t ws_bytes,
                                isb_stream_t stream)
@@ -301,7 +302,7 @@ extern "C" int isb_gc_energies(const double* proba, int N, int K, const int32_t*
     ISB_REQUIRE(!spatial || centres, "centres are required for spatially normalised edge weights");
     ISB_REQUIRE(ws_bytes >= isb_gc_energies_workspace_bytes(N, K, E), "workspace too small");
     ProfScope prof(ISB_PROF_ENERGY, (cudaStream_t)stream);
-    k_gc_energies<<<1, 1024, 0, (cudaStream_t)stream>>>(proba, N, K, edges, E, n_edges_dev, centres, proba, K, metric, spatial, edge_cost,
+    k_gc_energies<<<1, 1024, 0, (cudaStream_t)stream>>>(proba, N, n_nodes_dev, K, edges, E, n_edges_dev, centres, proba, K, metric, spatial, edge_cost,
                                                          pairwise, unary, edge_w, unary_i, edge_wi, smooth_i, (double*)ws);
     ISB_LAUNCH_CHECK();
     return ISB_OK;

@@ -183,7 +183,7 @@ class Engine(object):
                                          C.c_size_t(wsb), _lib.stream_ptr()))
         return edges, n_edges, cap
 
-    def gc_energies(self, d_proba, d_edges, E, d_n_edges, d_centres, edge_mode, edge_cost, pairwise):
+    def gc_energies(self, d_proba, d_edges, E, d_n_edges, d_centres, edge_mode, edge_cost, pairwise, d_n_nodes=None):
         torch, lib = self.torch, self.lib
         N, K = int(d_proba.shape[0]), int(d_proba.shape[1])
         d_pw = self.to_device(np.ascontiguousarray(pairwise, dtype=np.float64), 'pairwise')
@@ -194,13 +194,14 @@ class Engine(object):
         smooth_i = self.buf('smooth_i', (K, K), torch.int32)
         wsb = lib.isb_gc_energies_workspace_bytes(N, K, int(E))
         ws = self.buf('ws_energy', (wsb,), torch.uint8)
-        self._ck(lib.isb_gc_energies(_lib.ptr(d_proba), N, K, _lib.ptr(d_edges), int(E), _lib.ptr(d_n_edges), _lib.ptr(d_centres),
+        self._ck(lib.isb_gc_energies(_lib.ptr(d_proba), N, _lib.ptr(d_n_nodes), K, _lib.ptr(d_edges), int(E), _lib.ptr(d_n_edges), _lib.ptr(d_centres),
                                      int(edge_mode[0]), int(edge_mode[1]), C.c_double(edge_cost), _lib.ptr(d_pw), _lib.ptr(unary), _lib.ptr(edge_w),
                                      _lib.ptr(unary_i), _lib.ptr(edge_wi), _lib.ptr(smooth_i), _lib.ptr(ws), C.c_size_t(wsb),
                                      _lib.stream_ptr()))
         return unary, edge_w, unary_i, edge_wi, smooth_i
 
-    def alpha_expansion(self, N, K, E, d_n_edges, d_edges, edge_wi, unary_i, smooth_i, n_iter=-1, init_labels=None):
+    def alpha_expansion(self, N, K, E, d_n_edges, d_edges, edge_wi, unary_i, smooth_i, n_iter=-1, init_labels=None,
+                        d_n_nodes=None):
         torch, lib = self.torch, self.lib
         labels = self.buf('gc_labels', (N,), torch.int32)
         if init_labels is None:
@@ -211,10 +212,28 @@ class Engine(object):
         stats = self.buf('gc_stats', (4,), torch.int32)
         wsb = lib.isb_alpha_expansion_workspace_bytes(int(N), int(K), int(E))
         ws = self.buf('ws_gc', (wsb,), torch.uint8)
-        self._ck(lib.isb_alpha_expansion(int(N), int(K), int(E), _lib.ptr(d_n_edges), _lib.ptr(d_edges), _lib.ptr(edge_wi),
+        self._ck(lib.isb_alpha_expansion(int(N), _lib.ptr(d_n_nodes), int(K), int(E), _lib.ptr(d_n_edges), _lib.ptr(d_edges), _lib.ptr(edge_wi),
                                          _lib.ptr(unary_i), _lib.ptr(smooth_i), int(n_iter), _lib.ptr(labels), _lib.ptr(energy),
                                          _lib.ptr(stats), _lib.ptr(ws), C.c_size_t(wsb), _lib.stream_ptr()))
         return labels, energy, stats
+
+    def gmm_fit_predict(self, d_feat, K, n_init, max_iter, use_scaler=True, seed=0, d_n=None, init_labels=None, tol=1e-3,
+                        reg_covar=1e-6):
+        """device class model: returns (proba [N,K] device, params device vector; see isb_gmm_fit_predict)"""
+        torch, lib = self.torch, self.lib
+        N, D = int(d_feat.shape[0]), int(d_feat.shape[1])
+        ld = int(d_feat.stride(0))
+        proba = self.buf('proba', (N, K), torch.float64)
+        params = self.buf('gmm_params', (lib.isb_gmm_params_len(D, K),), torch.float64)
+        wsb = lib.isb_gmm_workspace_bytes(N, D, int(K), int(n_init))
+        ws = self.buf('ws_gmm', (wsb,), torch.uint8)
+        d_init = None
+        if init_labels is not None:
+            d_init = self.to_device(np.ascontiguousarray(init_labels, dtype=np.int32), 'gmm_init')
+        self._ck(lib.isb_gmm_fit_predict(_lib.ptr(d_feat), N, D, ld, _lib.ptr(d_n), int(K), int(n_init), int(max_iter), C.c_double(tol),
+                                         C.c_double(reg_covar), int(bool(use_scaler)), C.c_ulonglong(int(seed)), _lib.ptr(d_init),
+                                         _lib.ptr(proba), _lib.ptr(params), _lib.ptr(ws), C.c_size_t(wsb), _lib.stream_ptr()))
+        return proba, params
 
     def gather(self, d_seg, lut_i=None, lut_p=None):
         torch, lib = self.torch, self.lib

@@ -26,6 +26,12 @@ MIN_UNARY_PROB = 0.01
 MAX_PAIRWISE_COST = 1e5
 #: edge weights are clamped to [1 / val, val] (reference graph_cuts.py:40)
 MIN_MAX_EDGE_WEIGHT = 1e3
+#: the default 'GMM' class model is fitted on the GPU (isb_gmm_fit_predict) when it fits the device kernel
+#: (<= 16 features, <= 8 classes, no PCA); set False to force scikit-learn on the host
+USE_DEVICE_GMM = True
+#: seed of the device k-means++ initialisation (the reference leaves its model unseeded)
+RANDOM_SEED = 0
+DEVICE_GMM_MAX_FEATURES, DEVICE_GMM_MAX_CLASSES = 16, 8
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -100,6 +106,56 @@ def estim_class_model_kmeans(features, nb_classes, init_type='k-means++', max_it
     return gmm, y
 
 
+def device_gmm_applicable(nb_features, nb_classes, estim_model='GMM', pca_coef=None):
+    return (USE_DEVICE_GMM and estim_model == 'GMM' and pca_coef is None and nb_features <= DEVICE_GMM_MAX_FEATURES
+            and nb_classes <= DEVICE_GMM_MAX_CLASSES)
+
+
+def sklearn_pipeline_from_device(params, nb_features, nb_classes, nb_samples, use_scaler=True, n_init=1, max_iter=99):
+    """ wrap the parameters fitted by ``isb_gmm_fit_predict`` into the scikit-learn objects the reference returns
+    (Pipeline[StandardScaler?, GaussianMixture]) so that ``predict_proba`` & co. keep working on the host """
+    from sklearn import mixture, pipeline, preprocessing
+    p = np.asarray(params, dtype=np.float64)
+    D, K = int(nb_features), int(nb_classes)
+    mean, scale = p[:D].copy(), p[D:2 * D].copy()
+    o = 2 * D
+    weights = p[o:o + K].copy()
+    o += K
+    means = p[o:o + K * D].reshape(K, D).copy()
+    o += K * D
+    covs = p[o:o + K * D * D].reshape(K, D, D).copy()
+    o += K * D * D
+    prec_chol = p[o:o + K * D * D].reshape(K, D, D).copy()
+    o += K * D * D
+    lower, n_iter, converged, ok = p[o:o + 4]
+    if not ok:
+        raise ValueError('Fitting the mixture model failed because some components have ill-defined empirical covariance '
+                         '(for instance caused by singleton or collapsed samples). Try to decrease the number of components')
+    steps = []
+    if use_scaler:
+        sc = preprocessing.StandardScaler()
+        sc.mean_, sc.scale_, sc.var_ = mean, scale, scale ** 2
+        sc.n_features_in_, sc.n_samples_seen_ = D, int(nb_samples)
+        steps.append(('std_scaler', sc))
+    mm = mixture.GaussianMixture(n_components=K, covariance_type='full', n_init=n_init, max_iter=max_iter)
+    mm.weights_, mm.means_, mm.covariances_, mm.precisions_cholesky_ = weights, means, covs, prec_chol
+    mm.precisions_ = np.array([u @ u.T for u in prec_chol])
+    mm.converged_, mm.n_iter_, mm.lower_bound_, mm.n_features_in_ = bool(converged), int(n_iter), float(lower), D
+    steps.append(('model', mm))
+    return pipeline.Pipeline(steps)
+
+
+def estim_class_model_device(features, nb_classes, use_scaler=True, max_iter=99, init_labels=None, seed=None):
+    """ the default 'GMM' model fitted on the GPU; returns the same kind of object as :func:`estim_class_model` """
+    features = np.ascontiguousarray(features, dtype=np.float64)
+    eng = get_engine()
+    n_init = max(1, int(np.sqrt(max_iter))) if init_labels is None else len(np.atleast_2d(init_labels))
+    d_feat = eng.to_device(features, 'feat_in')
+    _, params = eng.gmm_fit_predict(d_feat, nb_classes, n_init, max_iter, use_scaler, RANDOM_SEED if seed is None else seed,
+                                    init_labels=None if init_labels is None else np.atleast_2d(init_labels))
+    return sklearn_pipeline_from_device(eng.to_host(params), features.shape[1], nb_classes, len(features), use_scaler, n_init, max_iter)
+
+
 def estim_class_model(features, nb_classes, estim_model='GMM', pca_coef=None, use_scaler=True, max_iter=99):
     """ scikit-learn pipeline (scaler, PCA, mixture model) fitted on the features (reference graph_cuts.py:73-163)
 
@@ -108,6 +164,11 @@ def estim_class_model(features, nb_classes, estim_model='GMM', pca_coef=None, us
     :param str estim_model: 'GMM', 'GMM_kmeans', 'GMM_Otsu', 'kmeans', 'kmeans_quantiles', 'BGM', 'Otsu'
     :return: fitted sklearn Pipeline with ``predict_proba``
     """
+    features = np.asarray(features)
+    if device_gmm_applicable(features.shape[1], nb_classes, estim_model, pca_coef):
+        import torch
+        if torch.cuda.is_available():
+            return estim_class_model_device(features, nb_classes, use_scaler, max_iter)
     from sklearn import cluster, decomposition, mixture, pipeline, preprocessing
     steps = []
     if use_scaler:

@@ -19,7 +19,8 @@ import numpy as np
 
 from .descriptors import FEATURES_SET_COLOR, compute_selected_features_img2d, flags_are_native
 from .engine import EDGE_MODES, get_engine
-from .graph_cuts import _edge_mode, compute_pairwise_cost, estim_class_model, segment_graph_cut_general
+from .graph_cuts import (_edge_mode, compute_pairwise_cost, device_gmm_applicable, estim_class_model,
+                         segment_graph_cut_general)
 from .superpixels import _as_rgb_like, _supported_dtype, device_adjacency, slic_params
 
 #: basic features extracted from superpixels (reference pipelines.py:35)
@@ -35,7 +36,7 @@ NB_WORKERS = 1
 
 class DeviceSuperpixels(object):
     """device-resident result of SLIC + descriptors for one image"""
-    __slots__ = ('d_img', 'd_seg', 'd_n_labels', 'nb_bound', 'd_feat', 'd_centres', 'shape')
+    __slots__ = ('d_img', 'd_seg', 'd_n_labels', 'nb_bound', 'd_feat', 'd_centres', 'shape', 'd_params', 'd_n_edges', 'edge_cap')
 
 
 def _device_slic_features(eng, image, dict_features, sp_size, sp_regul):
@@ -83,32 +84,81 @@ def compute_color2d_superpixels_features(image, dict_features, sp_size=30, sp_re
     return slic, features
 
 
-def _device_graphcut(eng, res, nb, proba, gc_regul, gc_edge_type, want_soft=True):
-    """device tail of the pipeline: adjacency, energies, alpha-expansion, LUT gathers"""
-    proba = np.ascontiguousarray(proba, dtype=np.float64)
-    K = proba.shape[1]
-    d_proba = eng.to_device(proba, 'proba')
-    pairwise = compute_pairwise_cost(gc_regul, proba.shape)
-    scalar = not isinstance(gc_regul, (list, np.ndarray))
-    d_soft = None
-    if scalar and gc_regul <= 0:
-        graph_labels = np.argmin(np.abs(-np.log(np.clip(proba, 0.01, 0.99))), axis=-1).astype(np.int32)
-        d_labels = eng.to_device(graph_labels, 'gc_labels_in')
-    else:
-        d_edges, E = device_adjacency(eng, res.d_seg, nb)
-        mode = _edge_mode(gc_edge_type)
-        _, _, unary_i, edge_wi, smooth_i = eng.gc_energies(d_proba, d_edges, E, None, res.d_centres, mode, 1.0, pairwise)
-        d_labels, _, _ = eng.alpha_expansion(nb, K, E, None, d_edges, edge_wi, unary_i, smooth_i, -1)
+def _device_graphcut(eng, res, nb, d_proba, K, gc_regul, gc_edge_type, d_n_nodes=None, want_soft=True, edge_cap=None):
+    """device tail of the pipeline: adjacency, energies, alpha-expansion, LUT gathers (all asynchronous).
+    ``nb`` may be an upper bound of the label count when ``d_n_nodes`` (device scalar) carries the real one.
+    Returns (d_labels, d_segm, d_soft, d_n_edges, edge_cap)."""
+    pairwise = compute_pairwise_cost(gc_regul, (nb, K))
+    d_edges, d_n_edges, edge_cap = eng.adjacency(res.d_seg, nb, edge_cap)
+    mode = _edge_mode(gc_edge_type)
+    _, _, unary_i, edge_wi, smooth_i = eng.gc_energies(d_proba, d_edges, edge_cap, d_n_edges, res.d_centres, mode, 1.0, pairwise,
+                                                       d_n_nodes=d_n_nodes)
+    d_labels, _, _ = eng.alpha_expansion(nb, K, edge_cap, d_n_edges, d_edges, edge_wi, unary_i, smooth_i, -1, d_n_nodes=d_n_nodes)
     d_segm, d_soft = eng.gather(res.d_seg, d_labels, d_proba if want_soft else None)
-    return d_labels, d_segm, d_soft
+    return d_labels, d_segm, d_soft, d_n_edges, edge_cap
 
 
-def _segment_with_proba_fn(image, proba_fn, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type, debug_visual, classes=None):
+def _argmin_labels_device(eng, proba):
+    graph_labels = np.argmin(np.abs(-np.log(np.clip(proba, 0.01, 0.99))), axis=-1).astype(np.int32)
+    return eng.to_device(graph_labels, 'gc_labels_in')
+
+
+#: initial capacity of the device edge table, in edges per (upper bound of) superpixel; grown x4 on overflow
+EDGE_CAP_PER_NODE = [8]
+
+
+def _run_resident(eng, image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type):
+    """the whole hot path on the device.  ``model`` is either ('fit', nb_classes, use_scaler, max_iter) -> the default
+    GMM is fitted on the GPU and NOTHING syncs with the host until the results are ready; or a callable
+    proba_fn(features) -> one round trip (features down, probabilities up) as in the reference.
+    Returns (d_segm, d_soft, check): ``check`` is None or (d_n_edges, edge_cap) still to be verified by the caller."""
+    res = _device_slic_features(eng, image, dict_features, sp_size, sp_regul)
+    no_cut = (not isinstance(gc_regul, (list, np.ndarray))) and gc_regul <= 0
+    if isinstance(model, tuple):
+        _, nb_classes, use_scaler, max_iter = model
+        from . import graph_cuts
+        n_init = max(1, int(np.sqrt(max_iter)))
+        d_proba, _ = eng.gmm_fit_predict(res.d_feat, nb_classes, n_init, max_iter, use_scaler, graph_cuts.RANDOM_SEED,
+                                         d_n=res.d_n_labels)
+        if no_cut:
+            nb = int(eng.to_host(res.d_n_labels)[0])
+            d_labels = _argmin_labels_device(eng, eng.to_host(d_proba[:nb]))
+            return eng.gather(res.d_seg, d_labels, d_proba) + (None, )
+        cap = max(64, EDGE_CAP_PER_NODE[0] * res.nb_bound)
+        _, d_segm, d_soft, d_n_edges, cap = _device_graphcut(eng, res, res.nb_bound, d_proba, nb_classes, gc_regul, gc_edge_type,
+                                                             d_n_nodes=res.d_n_labels, edge_cap=cap)
+        return d_segm, d_soft, (d_n_edges, cap)
+    nb = int(eng.to_host(res.d_n_labels)[0])
+    features = eng.to_host(res.d_feat[:nb]).copy()
+    features[np.isnan(features)] = 0
+    proba = np.ascontiguousarray(model(features), dtype=np.float64)
+    logging.debug('list of probabilities: %r', proba.shape)
+    d_proba = eng.to_device(proba, 'proba')
+    if no_cut:
+        return eng.gather(res.d_seg, _argmin_labels_device(eng, proba), d_proba) + (None, )
+    cap = max(64, EDGE_CAP_PER_NODE[0] * nb)
+    _, d_segm, d_soft, d_n_edges, cap = _device_graphcut(eng, res, nb, d_proba, proba.shape[1], gc_regul, gc_edge_type, edge_cap=cap)
+    return d_segm, d_soft, (d_n_edges, cap)
+
+
+def _download_results(eng, tensors):
+    """D2H into pinned buffers with ONE synchronisation; returns numpy views"""
+    outs = []
+    for t in tensors:
+        h = eng.pinned_empty(t.shape, t.dtype)
+        h.copy_(t, non_blocking=True)
+        outs.append(h)
+    eng.torch.cuda.current_stream().synchronize()
+    return [h.numpy() for h in outs]
+
+
+def _segment(image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type, debug_visual, classes=None):
     image = np.asarray(image)
     eng = get_engine()
     native = image.ndim == 3 and flags_are_native(dict_features) and gc_edge_type not in ('color', 'features')
     if not native or debug_visual is not None:
         # general path: every stage still runs on the device, but through the numpy-facing stage functions
+        proba_fn = model if callable(model) else (lambda f: estim_class_model(f, model[1], 'GMM', None, model[2], model[3]).predict_proba(f))
         slic, features = compute_color2d_superpixels_features(image, dict_features, sp_size=sp_size, sp_regul=sp_regul)
         if debug_visual is not None:
             img3 = image if image.ndim == 3 else np.stack([image] * 3, axis=-1)
@@ -122,36 +172,25 @@ def _segment_with_proba_fn(image, proba_fn, dict_features, sp_size, sp_regul, gc
         if classes is not None:
             graph_labels = classes[graph_labels]
         return graph_labels[slic], segm_soft
-    res = _device_slic_features(eng, image, dict_features, sp_size, sp_regul)
-    nb = int(eng.to_host(res.d_n_labels)[0])
-    features = eng.to_host(res.d_feat[:nb]).copy()
-    features[np.isnan(features)] = 0
-    proba = proba_fn(features)
-    logging.debug('list of probabilities: %r', proba.shape)
-    d_labels, d_segm, d_soft = _device_graphcut(eng, res, nb, proba, gc_regul, gc_edge_type)
-    torch = eng.torch
-    segm_h = eng.pinned_empty(d_segm.shape, d_segm.dtype)
-    soft_h = eng.pinned_empty(d_soft.shape, d_soft.dtype)
-    segm_h.copy_(d_segm, non_blocking=True)
-    soft_h.copy_(d_soft, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    segm = segm_h.numpy()
+    while True:
+        d_segm, d_soft, check = _run_resident(eng, image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)
+        if check is None:
+            segm, soft = _download_results(eng, (d_segm, d_soft))
+            break
+        segm, soft, n_edges = _download_results(eng, (d_segm, d_soft, check[0]))
+        if int(n_edges[0]) <= check[1]:
+            break
+        EDGE_CAP_PER_NODE[0] *= 4  # the device edge table overflowed (> 8 edges per superpixel on average): redo larger
     if classes is not None:
         segm = np.asarray(classes)[segm]
-    return segm, soft_h.numpy()
+    return segm, soft
 
 
-def segment_resident(d_image, proba_fn, dict_features, sp_size=30, sp_regul=0.2, gc_regul=1., gc_edge_type='model'):
+def segment_resident(d_image, model, dict_features, sp_size=30, sp_regul=0.2, gc_regul=1., gc_edge_type='model'):
     """ the same hot path with the image ALREADY on the device (a cuda tensor [H, W, 3]) and the results left
-    there: returns (segm int32 [H, W], segm_soft float64 [H, W, K]) device tensors.  ``proba_fn`` maps the host
-    feature matrix [N, D] to class probabilities [N, K] (fit + predict for the unsupervised pipeline). """
-    eng = get_engine()
-    res = _device_slic_features(eng, d_image, dict_features, sp_size, sp_regul)
-    nb = int(eng.to_host(res.d_n_labels)[0])
-    features = eng.to_host(res.d_feat[:nb]).copy()
-    features[np.isnan(features)] = 0
-    _, d_segm, d_soft = _device_graphcut(eng, res, nb, proba_fn(features), gc_regul, gc_edge_type)
-    return d_segm, d_soft
+    there: returns (segm int32 [H, W], segm_soft float64 [H, W, K]) device tensors.  ``model`` is a callable
+    proba_fn(features) or ('fit', nb_classes, use_scaler, max_iter) for the GPU-fitted default GMM. """
+    return _run_resident(get_engine(), d_image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)[:2]
 
 
 def pipe_color2d_slic_features_model_graphcut(image, nb_classes, dict_features, sp_size=30, sp_regul=0.2, pca_coef=None,
@@ -166,13 +205,13 @@ def pipe_color2d_slic_features_model_graphcut(image, nb_classes, dict_features, 
     :return tuple(ndarray,ndarray): segmentation [H, W] int32, soft segmentation [H, W, nb_classes] float64
     """
     logging.info('PIPELINE Superpixels-Features-GMM-GraphCut')
-    holder = {}
-
-    def _fit_predict(features):
-        holder['model'] = estim_class_model(features, nb_classes, estim_model, pca_coef, use_scaler)
-        return holder['model'].predict_proba(features)
-
-    return _segment_with_proba_fn(image, _fit_predict, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type, debug_visual)
+    nb_fts = 3 * len([f for f in dict_features.get('color', ()) if f in ('mean', 'std', 'energy')])
+    if flags_are_native(dict_features) and device_gmm_applicable(nb_fts, nb_classes, estim_model, pca_coef):
+        model = ('fit', nb_classes, use_scaler, 99)
+    else:
+        def model(features):
+            return estim_class_model(features, nb_classes, estim_model, pca_coef, use_scaler).predict_proba(features)
+    return _segment(image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type, debug_visual)
 
 
 def estim_model_classes_group(list_images, nb_classes, dict_features, sp_size=30, sp_regul=0.2, use_scaler=True,
@@ -199,5 +238,5 @@ def segment_color2d_slic_features_model_graphcut(image, model_pipeline, dict_fea
     """
     logging.info('PIPELINE Superpixels-Features-Model-GraphCut')
     classes = getattr(model_pipeline, 'classes_', None)
-    return _segment_with_proba_fn(image, model_pipeline.predict_proba, dict_features, sp_size, sp_regul, gc_regul,
-                                  gc_edge_type, debug_visual, classes=classes)
+    return _segment(image, model_pipeline.predict_proba, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type, debug_visual,
+                    classes=classes)

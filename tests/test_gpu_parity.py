@@ -176,3 +176,64 @@ def test_pipeline_with_shared_model_equals_oracle(oracle):
     segm2, soft2 = pl.pipe_color2d_slic_features_model_graphcut(img, 3, feats, sp_size=24)
     assert segm2.shape == img.shape[:2] and soft2.shape == img.shape[:2] + (3,)
     np.testing.assert_allclose(soft2.sum(-1), 1.0, rtol=1e-9)
+
+
+def test_device_gmm_matches_sklearn_from_shared_start():
+    """estim_class_model (imsegm/graph_cuts.py:73-163): same EM as sklearn's GaussianMixture when both start from the
+    same hard assignment; tolerance 1e-6 on parameters and probabilities (EM amplifies summation-order noise)"""
+    from sklearn import mixture, preprocessing
+    from pyimsegm_b200 import graph_cuts as gc
+    rng = np.random.RandomState(3)
+    K, D = 3, 3
+    centers = np.array([[0.2, 0.25, 0.18], [0.5, 0.52, 0.47], [0.8, 0.83, 0.78]])
+    X = np.concatenate([c + rng.normal(0, 0.04, (n, D)) for c, n in zip(centers, (1500, 2200, 1300))])
+    y0 = rng.randint(0, K, len(X))
+    y0[:60] = np.repeat(np.arange(K), 20)
+    near = ((X[:, None, :] - centers[None]) ** 2).sum(-1).argmin(1)
+    y0[::2] = near[::2]                       # a half-informed start so that EM has real work to do
+    model = gc.estim_class_model_device(X, K, use_scaler=True, max_iter=99, init_labels=y0)
+    scaler, gmm = model.named_steps['std_scaler'], model.named_steps['model']
+    Xs = preprocessing.StandardScaler().fit(X)
+    np.testing.assert_allclose(scaler.mean_, Xs.mean_, rtol=1e-12)
+    np.testing.assert_allclose(scaler.scale_, Xs.scale_, rtol=1e-12)
+    Z = Xs.transform(X)
+    resp = np.eye(K)[y0]
+    nk = resp.sum(0) + 10 * np.finfo(float).eps
+    means0 = resp.T @ Z / nk[:, None]
+    covs0 = np.array([((resp[:, k, None] * (Z - means0[k])).T @ (Z - means0[k])) / nk[k] + 1e-6 * np.eye(D) for k in range(K)])
+    ref = mixture.GaussianMixture(K, covariance_type='full', max_iter=99, n_init=1, weights_init=nk / len(Z), means_init=means0,
+                                  precisions_init=np.linalg.inv(covs0)).fit(Z)
+    assert gmm.n_iter_ == ref.n_iter_ and gmm.converged_ == ref.converged_
+    np.testing.assert_allclose(gmm.weights_, ref.weights_, rtol=1e-6)
+    np.testing.assert_allclose(gmm.means_, ref.means_, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(gmm.covariances_, ref.covariances_, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(gmm.lower_bound_, ref.lower_bound_, rtol=1e-8)
+    np.testing.assert_allclose(model.predict_proba(X), ref.predict_proba(Z), rtol=1e-5, atol=1e-9)
+    # the unseeded-in-the-reference default: k-means++ start on the device, 9 restarts; must separate the three blobs
+    model2 = gc.estim_class_model(X, K)
+    lab = model2.predict_proba(X).argmax(1)
+    assert len(model2.named_steps['model'].weights_) == K
+    purity = sum(np.bincount(lab[near == k], minlength=K).max() for k in range(K)) / len(X)
+    assert purity > 0.98
+
+
+def test_fully_resident_pipeline_is_consistent(oracle):
+    """pipe_color2d_slic_features_model_graphcut with the device-fitted GMM: its own model, replayed through the
+    shared-model entry point and through the oracle, must give the identical label map"""
+    from pyimsegm_b200 import graph_cuts as gc
+    from pyimsegm_b200 import pipelines as pl
+    img, truth = synth_regions(320, 448, seed=11)
+    feats = {'color': ['mean']}
+    segm, soft = pl.pipe_color2d_slic_features_model_graphcut(img, 3, feats, sp_size=20, sp_regul=0.2, gc_regul=1.)
+    assert segm.dtype == np.int32 and segm.shape == img.shape[:2] and soft.shape == img.shape[:2] + (3,)
+    np.testing.assert_allclose(soft.sum(-1), 1.0, rtol=1e-9)
+    # segmentation quality on the synthetic regions (labels are a permutation of the classes)
+    conf = np.array([[np.sum((segm == a) & (truth == b)) for b in range(3)] for a in range(3)])
+    assert conf.max(0).sum() / truth.size > 0.95
+    # replay: fit the same model through the public estimator (same seed, same features) and use entry point 3.2
+    slic, fts = pl.compute_color2d_superpixels_features(img, feats, sp_size=20, sp_regul=0.2)
+    model = gc.estim_class_model(fts, 3)
+    segm2, soft2 = pl.segment_color2d_slic_features_model_graphcut(img, model, feats, sp_size=20, sp_regul=0.2, gc_regul=1.)
+    assert np.array_equal(segm, segm2)
+    segm_o, _, _, _ = oracle.segment_with_model(img, model.predict_proba, ('mean',), 20, 0.2, 1., 'model')
+    assert np.array_equal(segm, segm_o)
