@@ -209,7 +209,7 @@ class Engine(object):
         else:
             labels.copy_(init_labels)
         energy = self.buf('gc_energy', (1,), torch.int64)
-        stats = self.buf('gc_stats', (4,), torch.int32)
+        stats = self.buf('gc_stats', (8,), torch.int32)
         wsb = lib.isb_alpha_expansion_workspace_bytes(int(N), int(K), int(E))
         ws = self.buf('ws_gc', (wsb,), torch.uint8)
         self._ck(lib.isb_alpha_expansion(int(N), _lib.ptr(d_n_nodes), int(K), int(E), _lib.ptr(d_n_edges), _lib.ptr(d_edges), _lib.ptr(edge_wi),
