@@ -23,8 +23,11 @@
 namespace {
 
 constexpr int TILE = 32;   // pixel tile edge of the assignment kernel
-constexpr int ACAP = 96;   // candidate clusters staged per round
-constexpr int AROWS = 4;   // pixels per thread (same column, rows ty, ty+8, ty+16, ty+24)
+constexpr int ACAP = 128;  // candidate clusters staged per round
+constexpr int AROWS = 8;   // consecutive rows per thread (same column)
+constexpr int AWARPS = TILE / AROWS;      // 4 warps
+constexpr int ATHREADS = 32 * AWARPS;     // 128 threads per tile
+
 
 struct __align__(16) Cand {
     double cy, cx, c0, c1, c2;
@@ -37,13 +40,14 @@ struct KmState {
     // cluster state (SoA)
     double* cy; double* cx; double* c0; double* c1; double* c2;
     int4* win;       // [n] (y0, y1, x0, x1); empty (0,0,0,0) when dead
-    int4* obb;       // [n] bbox of orphan pixels (ymin, ymax, xmin, xmax), empty = (INT_MAX, -1, INT_MAX, -1)
+    int4* obb;       // [n] bbox of the cluster's member pixels (ymin, ymax, xmin, xmax), empty = (INT_MAX, -1, INT_MAX, -1)
     double* sums;    // [n][3] colour sums of the current update
     long long* isum; // [n][3] count, sum y, sum x
     int* bin_start;  // [nbins + 1]
     int* bin_fill;   // [nbins]
     int* bin_items;  // [n]
     int* bin_of;     // [n]
+    Cand* packed;    // [n] cluster records in bin order (what k_assign streams)
     int n, H, W, step_y, step_x, B, nby, nbx;
     double sw;       // spatial weight 1/step^2
 };
@@ -103,92 +107,146 @@ __global__ void __launch_bounds__(1024) k_finalize_bin(KmState s, const double* 
         s.obb[k] = make_int4(INT_MAX, -1, INT_MAX, -1);
     }
     __syncthreads();
-    // exclusive scan of bin counts (block-wide, chunked)
-    __shared__ int s_part[1024];
+    // exclusive scan of bin counts: warp shuffles + one partial per warp, chunks of blockDim
+    __shared__ int s_wsum[32];
+    __shared__ int s_part_total;
     __shared__ int s_carry;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int base = 0; base < nbins; base += blockDim.x) {
         int b = base + threadIdx.x;
         int v = b < nbins ? s.bin_fill[b] : 0;
-        s_part[threadIdx.x] = v;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_wsum[wid] = incl;
         __syncthreads();
-        for (int o = 1; o < (int)blockDim.x; o <<= 1) {
-            int t = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
-            __syncthreads();
-            s_part[threadIdx.x] += t;
-            __syncthreads();
+        if (wid == 0) {
+            int t = lane < nw ? s_wsum[lane] : 0, ti = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, ti, o); if (lane >= o) ti += u; }
+            s_wsum[lane] = ti - t; // exclusive prefix of the warp sums
+            if (lane == 31) s_part_total = ti;
         }
-        int incl = s_part[threadIdx.x];
-        int carry = s_carry;
-        if (b < nbins) { s.bin_start[b] = carry + incl - v; s.bin_fill[b] = 0; }
         __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_carry = carry + incl;
+        const int carry = s_carry;
+        if (b < nbins) { s.bin_start[b] = carry + s_wsum[wid] + incl - v; s.bin_fill[b] = 0; }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + s_part_total;
         __syncthreads();
     }
     if (threadIdx.x == 0) s.bin_start[nbins] = s_carry;
     __syncthreads();
     for (int k = threadIdx.x; k < s.n; k += blockDim.x) {
         int bin = s.bin_of[k];
-        if (bin >= 0) s.bin_items[s.bin_start[bin] + atomicAdd(&s.bin_fill[bin], 1)] = k;
+        if (bin < 0) continue;
+        const int pos = s.bin_start[bin] + atomicAdd(&s.bin_fill[bin], 1);
+        s.bin_items[pos] = k;
+        const int4 w = s.win[k];
+        Cand c;
+        c.cy = s.cy[k]; c.cx = s.cx[k]; c.c0 = s.c0[k]; c.c1 = s.c1[k]; c.c2 = s.c2[k];
+        c.y0 = w.x; c.y1 = w.y; c.x0 = w.z; c.x1 = w.w; c.k = k; c.pad = 0;
+        s.packed[pos] = c;
     }
 }
 
-// assignment: one CTA per 32x32 tile, 256 threads, 4 pixels per thread
-__global__ void __launch_bounds__(256) k_assign(KmState s, const double* __restrict__ lab, int* __restrict__ labels)
+// non-negative doubles order like their bit patterns: compare on the integer pipe instead of the FP64 pipe
+// (unsigned, so that a NaN of either sign ranks above every number and can never win)
+__device__ __forceinline__ unsigned long long dbits(double v) { return (unsigned long long)__double_as_longlong(v); }
+
+// assignment: one CTA (128 threads) per 32x32 tile; a thread owns one column and AROWS = 8 consecutive rows.
+// The tile's Lab values are staged in shared memory, candidates are visited nearest-first and the loop stops as soon as
+// the spatial lower bound of every remaining candidate exceeds the worst of the thread's current minima.
+__global__ void __launch_bounds__(ATHREADS) k_assign(KmState s, const double* __restrict__ lab, int* __restrict__ labels)
 {
     __shared__ Cand cand[ACAP];
-    __shared__ int s_ncand, s_done, s_row, s_off;
+    __shared__ float s_key[ACAP];
+    __shared__ double s_lb[ACAP];          // lower bound of the spatial term of the candidate at sorted position i, and of all later ones
+    __shared__ unsigned char s_order[ACAP];
+    __shared__ double s_px[3][TILE][TILE]; // Lab of the tile
+    __shared__ int s_ncand, s_done, s_row, s_off, s_total;
     const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
     const int tx1 = min(tx0 + TILE, s.W), ty1 = min(ty0 + TILE, s.H);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t HW = (size_t)s.H * s.W;
     const int x = tx0 + lane;
     const bool xin = x < s.W;
+    const int yb = ty0 + warp * AROWS; // first row of this thread
 
-    double p0[AROWS], p1[AROWS], p2[AROWS], best[AROWS];
+    double best[AROWS];
     int bestk[AROWS];
+    {
+        double v[3][AROWS];
 #pragma unroll
-    for (int j = 0; j < AROWS; ++j) {
-        int y = ty0 + warp + 8 * j;
-        best[j] = DBL_MAX; bestk[j] = -1;
-        if (xin && y < s.H) {
-            size_t p = (size_t)y * s.W + x;
-            p0[j] = lab[p]; p1[j] = lab[HW + p]; p2[j] = lab[2 * HW + p];
-        } else { p0[j] = p1[j] = p2[j] = 0.0; }
+        for (int j = 0; j < AROWS; ++j) {
+            const int y = yb + j;
+            best[j] = DBL_MAX; bestk[j] = -1;
+            if (xin && y < s.H) {
+                const size_t p = (size_t)y * s.W + x;
+                v[0][j] = lab[p]; v[1][j] = lab[HW + p]; v[2][j] = lab[2 * HW + p];
+            } else { v[0][j] = v[1][j] = v[2][j] = 0.0; }
+        }
+#pragma unroll
+        for (int j = 0; j < AROWS; ++j) {
+            s_px[0][warp * AROWS + j][lane] = v[0][j]; s_px[1][warp * AROWS + j][lane] = v[1][j]; s_px[2][warp * AROWS + j][lane] = v[2][j];
+        }
     }
     // bins that can hold a centroid whose window reaches this tile (superset; the exact window test follows)
     const int by0 = max(ty0 - 2 * s.step_y - 2, 0) / s.B, by1 = min(ty1 + 2 * s.step_y + 1, s.H - 1) / s.B;
     const int bx0 = max(tx0 - 2 * s.step_x - 2, 0) / s.B, bx1 = min(tx1 + 2 * s.step_x + 1, s.W - 1) / s.B;
-    if (threadIdx.x == 0) { s_row = by0; s_off = 0; s_done = 0; }
+    const float tcy = 0.5f * (ty0 + ty1 - 1), tcx = 0.5f * (tx0 + tx1 - 1);
+    const int byl = min(by1, s.nby - 1), bxl = min(bx1, s.nbx - 1);
+    // how many clusters sit in the bin rows that can reach this tile (bins of one row are contiguous in bin order)
+    if (threadIdx.x == 0) { s_row = by0; s_off = 0; s_done = 0; s_ncand = 0; s_total = 0; }
     __syncthreads();
+    if (warp == 0) {
+        int t = 0;
+        for (int row = by0 + lane; row <= byl; row += 32) t += s.bin_start[row * s.nbx + bxl + 1] - s.bin_start[row * s.nbx + bx0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) s_total = t;
+    }
+    __syncthreads();
+    const bool fast = s_total <= ACAP; // everything fits in one round: all warps build the list together
 
     while (true) {
-        if (warp == 0) {
-            // deterministic, resumable scan of the bin rows: fill up to ACAP candidates
+        if (fast) {
+            for (int row = by0 + warp; row <= byl; row += AWARPS) {
+                const int beg = s.bin_start[row * s.nbx + bx0], end = s.bin_start[row * s.nbx + bxl + 1];
+                for (int i = beg + lane; i < end; i += 32) {
+                    const Cand c = s.packed[i];
+                    if ((c.y0 < ty1) && (c.y1 > ty0) && (c.x0 < tx1) && (c.x1 > tx0)) {
+                        const int pos = atomicAdd(&s_ncand, 1);
+                        cand[pos] = c;
+                        const float fy = (float)c.cy - tcy, fx = (float)c.cx - tcx;
+                        s_key[pos] = fy * fy + fx * fx;
+                    }
+                }
+            }
+            if (threadIdx.x == 0) s_done = 1;
+        } else if (warp == 0) {
+            // deterministic, resumable scan of the bin rows: fill up to ACAP candidates per round
             int n = 0;
             int row = s_row, off = s_off;
-            while (row <= min(by1, s.nby - 1) && n < ACAP) {
+            while (row <= byl && n < ACAP) {
                 int beg = s.bin_start[row * s.nbx + bx0] + off;
-                int end = s.bin_start[row * s.nbx + min(bx1, s.nbx - 1) + 1];
+                int end = s.bin_start[row * s.nbx + bxl + 1];
                 while (beg < end && n < ACAP) {
                     int room = ACAP - n;
                     int i = beg + lane;
                     bool ok = false;
-                    int k = -1;
-                    int4 w;
+                    Cand c;
                     if (i < end && lane < room) {
-                        k = s.bin_items[i];
-                        w = s.win[k];
-                        ok = (w.x < ty1) && (w.y > ty0) && (w.z < tx1) && (w.w > tx0);
+                        c = s.packed[i];
+                        ok = (c.y0 < ty1) && (c.y1 > ty0) && (c.x0 < tx1) && (c.x1 > tx0);
                     }
                     unsigned m = __ballot_sync(0xffffffffu, ok);
                     if (ok) {
                         int pos = n + __popc(m & ((1u << lane) - 1u));
-                        Cand c;
-                        c.cy = s.cy[k]; c.cx = s.cx[k]; c.c0 = s.c0[k]; c.c1 = s.c1[k]; c.c2 = s.c2[k];
-                        c.y0 = w.x; c.y1 = w.y; c.x0 = w.z; c.x1 = w.w; c.k = k; c.pad = 0;
                         cand[pos] = c;
+                        const float fy = (float)c.cy - tcy, fx = (float)c.cx - tcx;
+                        s_key[pos] = fy * fy + fx * fx;
                     }
                     n += __popc(m);
                     int adv = min(min(32, room), end - beg);
@@ -196,51 +254,89 @@ __global__ void __launch_bounds__(256) k_assign(KmState s, const double* __restr
                 }
                 if (beg >= end) { ++row; off = 0; }
             }
-            if (lane == 0) { s_ncand = n; s_row = row; s_off = off; s_done = row > min(by1, s.nby - 1); }
+            if (lane == 0) { s_ncand = n; s_row = row; s_off = off; s_done = row > byl; }
         }
         __syncthreads();
         const int nc = s_ncand;
         const int done = s_done;
+        // nearest-first evaluation order (rank sort by distance of the centroid to the tile centre).  Any order gives the
+        // same result -- the minimum over (distance, index) is order independent.
+        for (int t = threadIdx.x; t < nc; t += ATHREADS) {
+            const float key = s_key[t];
+            int rank = 0;
+            for (int j = 0; j < nc; ++j) {
+                const float kj = s_key[j];
+                rank += (kj < key) || (kj == key && j < t);
+            }
+            s_order[rank] = (unsigned char)t;
+            // every pixel of the tile is within R of the tile centre, so a centroid at distance sqrt(key) from the centre is at
+            // least sqrt(key) - R from the pixel; the bound is relaxed (R rounded up, 0.1 % slack) so that float rounding can
+            // only make it smaller, i.e. it never rejects a candidate that could win or tie
+            const float r = sqrtf(key) - 23.5f;
+            s_lb[rank] = r > 0.f ? (double)(r * r * 0.999f) * s.sw * 0.999 : 0.0;
+        }
+        __syncthreads();
         if (xin) {
             const double xd = (double)x;
-            for (int c = 0; c < nc; ++c) {
+            unsigned long long worst = dbits(DBL_MAX); // max over the rows of the current minima (bit pattern)
+#pragma unroll
+            for (int j = 0; j < AROWS; ++j) worst = max(worst, dbits(best[j]));
+            for (int ci = 0; ci < nc; ++ci) {
+                if (dbits(s_lb[ci]) > worst) break; // sorted by key: nobody further down the list can win either
+                const int c = s_order[ci];
                 const int cx0 = cand[c].x0, cx1 = cand[c].x1;
                 if (x < cx0 || x >= cx1) continue;
                 const int cy0 = cand[c].y0, cy1 = cand[c].y1, ck = cand[c].k;
-                const double ccy = cand[c].cy, cc0 = cand[c].c0, cc1 = cand[c].c1, cc2 = cand[c].c2;
+                const double ccy = cand[c].cy;
                 const double tx = __dsub_rn(cand[c].cx, xd);
                 const double dx2 = __dmul_rn(tx, tx);
+                bool improved = false;
 #pragma unroll
                 for (int j = 0; j < AROWS; ++j) {
-                    const int y = ty0 + warp + 8 * j;
+                    const int y = yb + j;
                     if (y < cy0 || y >= cy1) continue;
                     const double ty = __dsub_rn(ccy, (double)y);
-                    double dc = __dmul_rn(__dadd_rn(__dmul_rn(ty, ty), dx2), s.sw);
-                    const double d0 = __dsub_rn(p0[j], cc0), d1 = __dsub_rn(p1[j], cc1), d2 = __dsub_rn(p2[j], cc2);
+                    const double sp = __dmul_rn(__dadd_rn(__dmul_rn(ty, ty), dx2), s.sw);
+                    // exact pruning: the colour term is >= 0 and fl(a + b) >= a for b >= 0, so d >= sp > best cannot win or tie
+                    if (dbits(sp) > dbits(best[j])) continue;
+                    const int ry = warp * AROWS + j;
+                    const double d0 = __dsub_rn(s_px[0][ry][lane], cand[c].c0), d1 = __dsub_rn(s_px[1][ry][lane], cand[c].c1),
+                                 d2 = __dsub_rn(s_px[2][ry][lane], cand[c].c2);
                     double dcol = __dmul_rn(d0, d0);
                     dcol = __dadd_rn(dcol, __dmul_rn(d1, d1));
                     dcol = __dadd_rn(dcol, __dmul_rn(d2, d2));
-                    dc = __dadd_rn(dc, dcol);
-                    if (dc < best[j] || (dc == best[j] && bestk[j] >= 0 && ck < bestk[j])) { best[j] = dc; bestk[j] = ck; }
+                    const double dc = __dadd_rn(sp, dcol);
+                    const unsigned long long bd = dbits(dc), bb = dbits(best[j]);
+                    if (bd < bb || (bd == bb && bestk[j] >= 0 && ck < bestk[j])) { best[j] = dc; bestk[j] = ck; improved = true; }
+                }
+                if (improved) {
+                    worst = 0;
+#pragma unroll
+                    for (int j = 0; j < AROWS; ++j) if (yb + j < s.H) worst = max(worst, dbits(best[j]));
                 }
             }
         }
         if (done) break;
         __syncthreads();
     }
-    if (xin) {
 #pragma unroll
-        for (int j = 0; j < AROWS; ++j) {
-            int y = ty0 + warp + 8 * j;
-            if (y >= s.H) continue;
-            size_t p = (size_t)y * s.W + x;
-            if (bestk[j] >= 0) labels[p] = bestk[j];
-            else {
-                // no window holds this pixel: it keeps its label (the original leaves nearest_segments untouched);
-                // tell that cluster's update where to look
-                int k = labels[p];
+    for (int j = 0; j < AROWS; ++j) {
+        const int y = yb + j;
+        const bool in = xin && y < s.H;     // y is warp-uniform
+        int k = -1;
+        if (in) {
+            const size_t p = (size_t)y * s.W + x;
+            if (bestk[j] >= 0) { k = bestk[j]; labels[p] = k; }
+            else k = labels[p];             // no window holds this pixel: it keeps its label (the original leaves it untouched)
+        }
+        // bounding box of every cluster's members (orphans included): one leader per (warp row, label) updates it
+        const unsigned act = __ballot_sync(0xffffffffu, in);
+        if (in) {
+            const unsigned grp = __match_any_sync(act, k);
+            if (lane == __ffs(grp) - 1) {
+                const int xa = tx0 + __ffs(grp) - 1, xb = tx0 + 31 - __clz(grp);
                 atomicMin(&s.obb[k].x, y); atomicMax(&s.obb[k].y, y);
-                atomicMin(&s.obb[k].z, x); atomicMax(&s.obb[k].w, x);
+                atomicMin(&s.obb[k].z, xa); atomicMax(&s.obb[k].w, xb);
             }
         }
     }
@@ -253,13 +349,9 @@ __global__ void __launch_bounds__(256) k_update(KmState s, const double* __restr
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int k = blockIdx.x * 8 + wl;
     if (k >= s.n) return;
-    int4 w = s.win[k];
-    int4 o = s.obb[k];
-    int y0 = w.x, y1 = w.y, x0 = w.z, x1 = w.w;
-    if (o.y >= o.x) { // orphans: grow the scan box
-        if (y1 <= y0 || x1 <= x0) { y0 = o.x; y1 = o.y + 1; x0 = o.z; x1 = o.w + 1; }
-        else { y0 = min(y0, o.x); y1 = max(y1, o.y + 1); x0 = min(x0, o.z); x1 = max(x1, o.w + 1); }
-    }
+    // the box of this cluster's members, gathered by k_assign (empty when the cluster has no pixel)
+    const int4 o = s.obb[k];
+    const int y0 = o.x, y1 = o.y + 1, x0 = o.z, x1 = o.w + 1;
     const size_t HW = (size_t)s.H * s.W;
     double acc = 0.0;
     long long cnt = 0, sy = 0, sx = 0;
@@ -314,6 +406,7 @@ static size_t carve(KmState& s, void* ws, size_t bytes, int H, int W, int n, int
     s.bin_start = c.take<int>((size_t)s.nby * s.nbx + 1);
     s.bin_fill = c.take<int>((size_t)s.nby * s.nbx);
     s.bin_items = c.take<int>(n); s.bin_of = c.take<int>(n);
+    s.packed = c.take<Cand>(n);
     return isb_align(c.off);
 }
 
@@ -342,7 +435,7 @@ extern "C" int isb_slic_kmeans(const double* lab_planar, int H, int W, const dou
     ISB_LAUNCH_CHECK();
     dim3 agrid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE);
     for (int it = 0; it < max_iter; ++it) {
-        { ProfScope p(ISB_PROF_ASSIGN, st); k_assign<<<agrid, 256, 0, st>>>(s, lab_planar, labels); }
+        { ProfScope p(ISB_PROF_ASSIGN, st); k_assign<<<agrid, ATHREADS, 0, st>>>(s, lab_planar, labels); }
         ISB_LAUNCH_CHECK();
         { ProfScope p(ISB_PROF_UPDATE, st); k_update<<<(n_seeds + 7) / 8, 256, 0, st>>>(s, lab_planar, labels); }
         ISB_LAUNCH_CHECK();
