@@ -106,6 +106,11 @@ def dist_env():
 def _oracle_one(seed):
     import oracle
     from sklearn import mixture, pipeline, preprocessing
+    try:  # one BLAS/OpenMP thread per worker process: the pool already uses the cores (no oversubscription)
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except ImportError:
+        pass
     img = synth_image(seed)
     t0 = time.perf_counter()
     slic, fts = oracle.compute_color2d_superpixels_features(img, ('mean',), SP_SIZE, SP_REGUL)
