@@ -58,7 +58,7 @@ extern "C" int isb_profile_stage_count(void) { return ISB_PROF_COUNT; }
 extern "C" const char* isb_profile_stage_name(int id)
 {
     static const char* names[ISB_PROF_COUNT] = { "slic_prepare", "slic_assign", "slic_update", "slic_finalize_bin", "slic_connectivity",
-                                                 "segment_stats", "adjacency", "gc_energies", "alpha_expansion", "gather", "gmm" };
+                                                 "segment_stats", "adjacency", "gc_energies", "alpha_expansion", "gather", "gmm", "lm_texture" };
     return (id >= 0 && id < ISB_PROF_COUNT) ? names[id] : "";
 }
 

@@ -11,7 +11,7 @@ extern long long g_isb_launches;
 // stage timers (capi.cu): no-ops unless isb_profile_enable(1)
 enum {
     ISB_PROF_PREPARE = 0, ISB_PROF_ASSIGN, ISB_PROF_UPDATE, ISB_PROF_FINALIZE, ISB_PROF_CONN, ISB_PROF_STATS, ISB_PROF_ADJ,
-    ISB_PROF_ENERGY, ISB_PROF_GC, ISB_PROF_GATHER, ISB_PROF_GMM, ISB_PROF_COUNT
+    ISB_PROF_ENERGY, ISB_PROF_GC, ISB_PROF_GATHER, ISB_PROF_GMM, ISB_PROF_LM, ISB_PROF_COUNT
 };
 int isb_prof_begin(int id, cudaStream_t st);
 void isb_prof_end(int handle, cudaStream_t st);

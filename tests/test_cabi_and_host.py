@@ -27,7 +27,7 @@ def test_header_symbols_all_exported(built_lib):
         assert hasattr(handle, name), 'library does not export %s' % name
     assert declared == set(built_lib.SIGNATURES), 'ctypes binding table and header disagree'
     assert handle.isb_abi_version() >= 2
-    assert handle.isb_profile_stage_count() == 11
+    assert handle.isb_profile_stage_count() == 12
     assert handle.isb_launch_count() == 0
 
 
