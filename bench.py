@@ -217,9 +217,11 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), out
 
+    keep = None
     for _ in range(max(args.warmup, 3)):
         step_resident()
-        step_e2e()
+        keep = step_e2e()   # held across the next call, like `out = fn()` in the timed loop: warms BOTH sets of pinned result buffers
+    del keep
 
     sampler = ClockSampler(local)
     if rank == 0:

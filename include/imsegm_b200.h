@@ -162,6 +162,9 @@ int isb_lm_texture(const void* img, int dtype, const int32_t* seg, int H, int W,
                    const double* chmix_host, const float* w_hi, const float* w_lo, int NP, int orient, int n_batt, int flags,
                    double* feat, int ld, int col0, void* ws, size_t ws_bytes, isb_stream_t stream);
 
+/* dst[0..n) = value (initial labeling of isb_alpha_expansion and similar small fills) */
+int isb_fill_i32(int32_t* dst, long long n, int32_t value, isb_stream_t stream);
+
 /* final LUT gathers of imsegm/pipelines.py:104,109:  segm = graph_labels[slic], segm_soft = proba[slic]
  *   lut_i [nb] i32 (optional), lut_p [nb,K] f64 (optional); outputs [H,W] i32 / [H,W,K] f64 */
 int isb_gather(const int32_t* seg, long long npx, const int32_t* lut_i, const double* lut_p, int K, int32_t* out_i,

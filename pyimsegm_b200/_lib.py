@@ -44,6 +44,7 @@ SIGNATURES = {
     'isb_gmm_fit_predict': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _d, _d, _i, C.c_ulonglong, _vp, _vp, _vp, _vp, _sz, _vp]),
     'isb_lm_workspace_bytes': (_sz, [_i, _i, _i, _i]),
     'isb_lm_texture': (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, C.POINTER(_d), _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _sz, _vp]),
+    'isb_fill_i32': (_i, [_vp, _ll, _i, _vp]),
     'isb_gather': (_i, [_vp, _ll, _vp, _vp, _i, _vp, _vp, _vp]),
 }
 

@@ -308,6 +308,20 @@ extern "C" int isb_gc_energies(const double* proba, int N, const int32_t* n_node
     return ISB_OK;
 }
 
+__global__ void k_fill_i32(int* p, long long n, int v)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+extern "C" int isb_fill_i32(int32_t* dst, long long n, int32_t value, isb_stream_t stream)
+{
+    ISB_REQUIRE(dst && n > 0, "bad arguments");
+    k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dst, n, value);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
 extern "C" int isb_gather(const int32_t* seg, long long npx, const int32_t* lut_i, const double* lut_p, int K, int32_t* out_i,
                           double* out_p, isb_stream_t stream)
 {

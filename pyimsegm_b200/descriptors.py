@@ -256,5 +256,18 @@ def compute_selected_features_img2d(image, segm, features_flags=FEATURES_SET_COL
 
 
 def flags_are_native(dict_features):
-    """True when every requested statistic is one the device computes in a single resident pass"""
-    return all(k == 'color' and all(f in FLAG_BITS for f in v) for k, v in dict_features.items())
+    """True when every requested feature group / statistic is one the resident device path computes
+    ('color', 'tLM', 'tLM_short' with mean / std / energy)"""
+    return bool(dict_features) and all(k in ('color', 'tLM', 'tLM_short') and all(f in FLAG_BITS for f in v)
+                                       for k, v in dict_features.items())
+
+
+def native_feature_layout(dict_features):
+    """[(key, flags, first column, n columns)] in the reference's column order: colour groups first, then texture"""
+    layout, col = [], 0
+    for k in [k for k in dict_features if k.startswith('color')] + [k for k in dict_features if k.startswith('tLM')]:
+        flags = [f for f in ('mean', 'std', 'energy') if f in dict_features[k]]
+        n = 3 * len(flags) * (1 if k == 'color' else (15 if k.endswith('_short') else 20))
+        layout.append((k, flags, col, n))
+        col += n
+    return layout, col

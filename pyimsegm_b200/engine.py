@@ -205,9 +205,9 @@ class Engine(object):
         torch, lib = self.torch, self.lib
         labels = self.buf('gc_labels', (N,), torch.int32)
         if init_labels is None:
-            labels.zero_()
+            self._ck(lib.isb_fill_i32(_lib.ptr(labels), C.c_longlong(int(N)), 0, _lib.stream_ptr()))
         else:
-            labels.copy_(init_labels)
+            labels.copy_(init_labels)  # device-to-device memcpy of a caller-supplied labeling
         energy = self.buf('gc_energy', (1,), torch.int64)
         stats = self.buf('gc_stats', (8,), torch.int32)
         wsb = lib.isb_alpha_expansion_workspace_bytes(int(N), int(K), int(E))

@@ -17,7 +17,7 @@ import logging
 
 import numpy as np
 
-from .descriptors import FEATURES_SET_COLOR, compute_selected_features_img2d, flags_are_native
+from .descriptors import FEATURES_SET_COLOR, compute_selected_features_img2d, flags_are_native, native_feature_layout
 from .engine import EDGE_MODES, get_engine
 from .graph_cuts import (_edge_mode, compute_pairwise_cost, device_gmm_applicable, estim_class_model,
                          segment_graph_cut_general)
@@ -55,8 +55,19 @@ def _device_slic_features(eng, image, dict_features, sp_size, sp_regul):
     res.d_img = image if on_device else eng.to_device(image, 'image')
     res.d_seg, res.d_n_labels = eng.slic(res.d_img, n_seg, compact, sigma=1.0)
     res.nb_bound = eng.slic_label_bound(H, W, n_seg)
-    flags = [f for f in ('mean', 'std', 'energy') if f in dict_features.get('color', ())]
-    res.d_feat, res.d_centres, _ = eng.segment_stats(res.d_img, res.d_seg, res.nb_bound, flags, want_centres=True)
+    layout, ncol = native_feature_layout(dict_features)
+    res.d_feat = eng.buf('feat', (res.nb_bound, max(ncol, 1)), eng.torch.float64)
+    res.d_centres = None
+    for key, flags, col0, _ in layout:
+        if key == 'color':
+            _, res.d_centres, _ = eng.segment_stats(res.d_img, res.d_seg, res.nb_bound, flags, feat=res.d_feat, col0=col0,
+                                                    want_centres=True)
+        else:
+            from .texture import device_lm_features
+            device_lm_features(eng, res.d_img, res.d_seg, res.nb_bound, flags, 'short' if key.endswith('_short') else 'normal',
+                               feat=res.d_feat, col0=col0)
+    if res.d_centres is None:
+        _, res.d_centres, _ = eng.segment_stats(None, res.d_seg, res.nb_bound, (), want_centres=True)
     return res
 
 
@@ -205,7 +216,7 @@ def pipe_color2d_slic_features_model_graphcut(image, nb_classes, dict_features, 
     :return tuple(ndarray,ndarray): segmentation [H, W] int32, soft segmentation [H, W, nb_classes] float64
     """
     logging.info('PIPELINE Superpixels-Features-GMM-GraphCut')
-    nb_fts = 3 * len([f for f in dict_features.get('color', ()) if f in ('mean', 'std', 'energy')])
+    nb_fts = native_feature_layout(dict_features)[1] if flags_are_native(dict_features) else 10 ** 6
     if flags_are_native(dict_features) and device_gmm_applicable(nb_fts, nb_classes, estim_model, pca_coef):
         model = ('fit', nb_classes, use_scaler, 99)
     else:

@@ -110,3 +110,24 @@ def test_drop_in_alias_package():
     assert gc.MIN_MAX_EDGE_WEIGHT == 1e3 and gc.MIN_UNARY_PROB == 0.01 and gc.MAX_PAIRWISE_COST == 1e5
     with pytest.raises(ValueError):
         pl.compute_color2d_superpixels_features(np.zeros((32, 32, 3)), {'color': ['mean']}, sp_regul=0.)
+
+
+def test_color_space_shim_matches_reference_doctest():
+    """imsegm/descriptors.py:1227-1231: statistics of the HSV image (host conversion + host numpy statistics)"""
+    from pyimsegm_b200 import descriptors as ds
+    from pyimsegm_b200.color import convert_img_color_from_rgb
+    image = np.zeros((2, 10, 3))
+    image[:, 2:6, 0] = 1
+    image[:, 3:7, 1] = 3
+    image[:, 4:9, 2] = 2
+    segm = np.array([[0] * 5 + [1] * 5] * 2)
+    hsv = convert_img_color_from_rgb(image, 'hsv')
+    got = np.round(np.hstack([ds.numpy_img2d_color_mean(hsv, segm), ds.numpy_img2d_color_std(hsv, segm)]), 3)
+    assert got.tolist() == [[0.139, 0.533, 1.4, 0.176, 0.452, 1.356], [0.439, 0.733, 2., 0.244, 0.389, 1.095]]
+    assert convert_img_color_from_rgb(np.ones((50, 75, 3)), 'hsv').shape == (50, 75, 3)
+    assert convert_img_color_from_rgb(np.ones((5, 7, 3)), 'unknown').shape == (5, 7, 3)
+    rng = np.random.RandomState(0)
+    rgb = rng.random_sample((6, 9, 3))
+    lab = convert_img_color_from_rgb(rgb, 'lab')
+    assert 0 <= lab[..., 0].min() and lab[..., 0].max() <= 100
+    np.testing.assert_allclose(convert_img_color_from_rgb(np.full((2, 2, 3), 1.0), 'xyz')[0, 0], [0.950456, 1.0, 1.088754], rtol=1e-6)

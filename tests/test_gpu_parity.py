@@ -237,3 +237,43 @@ def test_fully_resident_pipeline_is_consistent(oracle):
     assert np.array_equal(segm, segm2)
     segm_o, _, _, _ = oracle.segment_with_model(img, model.predict_proba, ('mean',), 20, 0.2, 1., 'model')
     assert np.array_equal(segm, segm_o)
+
+
+def test_full_size_config2_bit_exact(oracle):
+    """BASELINE.json configs[1] at full size (2048x2048, sp_size 29, K = 3): SLIC label map and the final segmentation with
+    a shared model are identical to the oracle's, descriptors within 1e-6"""
+    from sklearn import mixture, pipeline, preprocessing
+    from pyimsegm_b200 import pipelines as pl
+    img, _ = synth_regions(2048, 2048, seed=2)
+    feats = {'color': ['mean']}
+    slic, fts = pl.compute_color2d_superpixels_features(img, feats, sp_size=29, sp_regul=0.2)
+    slic_o, fts_o = oracle.compute_color2d_superpixels_features(img, ('mean',), 29, 0.2)
+    assert np.array_equal(slic, slic_o)
+    np.testing.assert_allclose(fts, fts_o, rtol=1e-6, atol=1e-9)
+    assert 4500 < slic.max() + 1 < 5500
+    model = pipeline.Pipeline([('std_scaler', preprocessing.StandardScaler()),
+                               ('model', mixture.GaussianMixture(3, covariance_type='full', random_state=0))]).fit(fts_o)
+    segm, soft = pl.segment_color2d_slic_features_model_graphcut(img, model, feats, sp_size=29, sp_regul=0.2, gc_regul=1.)
+    proba = model.predict_proba(fts_o)
+    labels_o = oracle.segment_graph_cut_general(slic_o, proba, 1., 'model')
+    assert np.array_equal(segm, labels_o[slic_o])
+    np.testing.assert_allclose(soft[::7, ::5], proba[slic_o][::7, ::5], rtol=1e-6, atol=1e-9)
+
+
+def test_config1_reference_cpu_case(oracle):
+    """BASELINE.json configs[0]: 512x512 synthetic disc, 2 classes, sp_size 25"""
+    from pyimsegm_b200 import graph_cuts as gc
+    from pyimsegm_b200 import pipelines as pl
+    img = synth_disc(512, 512, seed=0)
+    feats = {'color': ['mean']}
+    segm, soft = pl.pipe_color2d_slic_features_model_graphcut(img, 2, feats, sp_size=25, sp_regul=0.2, gc_regul=1., gc_edge_type='model')
+    yy, xx = np.mgrid[:512, :512]
+    disc = (yy - 256) ** 2 + (xx - 256) ** 2 < 160 ** 2
+    agree = max(np.mean(segm == disc), np.mean(segm == ~disc))
+    assert agree > 0.98 and soft.shape == (512, 512, 2)
+    slic, fts = pl.compute_color2d_superpixels_features(img, feats, sp_size=25, sp_regul=0.2)
+    assert np.array_equal(slic, oracle.segment_slic_img2d(img, 25, 0.2))
+    model = gc.estim_class_model(fts, 2)
+    segm2, _ = pl.segment_color2d_slic_features_model_graphcut(img, model, feats, sp_size=25, sp_regul=0.2)
+    segm_o, _, _, _ = oracle.segment_with_model(img, model.predict_proba, ('mean',), 25, 0.2, 1., 'model')
+    assert np.array_equal(segm, segm2) and np.array_equal(segm2, segm_o)
