@@ -93,6 +93,22 @@ size_t isb_segment_stats_workspace_bytes(int nb);
 int isb_segment_stats_2d(const void* img, int dtype, const int32_t* seg, int H, int W, int nb, int flags, double* feat,
                          int ld, int col0, double* centres, int32_t* counts, void* ws, size_t ws_bytes, isb_stream_t stream);
 
+/* computeGrayImage3dMean :144 / Energy :169 / Variance :194 of features_cython.pyx: one channel, any rank (n voxels).
+ *   flags bit0 mean, bit1 std, bit2 energy -> columns col0.. of feat [nb, ld] in that order */
+size_t isb_gray_stats_workspace_bytes(int nb);
+int isb_gray_stats(const void* img, int dtype, const int32_t* seg, long long n, int nb, int flags, double* feat, int ld, int col0,
+                   void* ws, size_t ws_bytes, isb_stream_t stream);
+
+/* computeLabelHistogram2d (features_cython.pyx:222): hist[l] = #{p : segm_select[p] == l >= 0 and struc_elem[p] == 1} */
+int isb_label_hist_2d(const int16_t* segm_select, const int16_t* struc_elem, int H, int W, int nb_labels, uint32_t* hist,
+                      isb_stream_t stream);
+
+/* computeRayFeaturesBinary2d (features_cython.pyx:239) for n_pos positions at once: out [n_pos, n_ang] f32, -1 where the ray
+ * leaves the image, 0 where the position lies inside the border label (edge 'up').  sin_a / cos_a: the f32 sines and cosines
+ * of the ray angles as the reference forms them (np.deg2rad of the f32 angle, stored to float).  edge: 1 'up', -1 'down'. */
+int isb_ray_features_2d(const int8_t* seg_binary, int H, int W, const int32_t* positions, int n_pos, const float* sin_a,
+                        const float* cos_a, int n_ang, int edge, float* out, isb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * (iii) graph + energies + alpha-expansion
  * ------------------------------------------------------------------------------------------------------------------ */

@@ -384,3 +384,42 @@ def segment_with_model(image, predict_proba, flags=('mean',), sp_size=30, sp_reg
     proba = predict_proba(fts)
     labels = segment_graph_cut_general(slic_map, proba, gc_regul, edge_type, features=fts)
     return labels[slic_map], proba[slic_map], slic_map, fts
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# the remaining functions of imsegm/features_cython.pyx: gray 3-D statistics, label histogram, ray features
+# --------------------------------------------------------------------------------------------------------------------
+
+def gray3d_stat(img, seg, mode, mean=None):
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    seg = np.ascontiguousarray(seg, dtype=np.int32)
+    nb = int(seg.max()) + 1
+    out = np.zeros(nb, dtype=np.float64)
+    m = np.ascontiguousarray(mean, dtype=np.float32) if mode == 2 else None
+    lib().oracle_gray3d_stat(_p(img, C.c_float), _p(seg, C.c_int32), C.c_long(img.size), nb, mode,
+                             _p(m, C.c_float) if m is not None else None, _p(out, C.c_double))
+    return out
+
+
+def label_hist2d(segm_select, struc_elem, nb_labels):
+    a = np.ascontiguousarray(segm_select, dtype=np.int16)
+    b = np.ascontiguousarray(struc_elem, dtype=np.int16)
+    hist = np.zeros(int(nb_labels), dtype=np.uint32)
+    lib().oracle_label_hist2d(_p(a, C.c_int16), _p(b, C.c_int16), a.shape[0], a.shape[1], int(nb_labels), _p(hist, C.c_uint32))
+    return hist
+
+
+def ray_angles(angle_step):
+    """(sin, cos) as float32 exactly like features_cython.pyx:247-268 forms them"""
+    angles = np.arange(0, 360, angle_step, dtype=np.float32)
+    rads = [float(np.float32(np.deg2rad(a))) for a in angles]          # `rad` is a C float in the reference
+    return (np.array([np.sin(r) for r in rads], dtype=np.float32), np.array([np.cos(r) for r in rads], dtype=np.float32))
+
+
+def ray_features2d(seg_binary, position, angle_step=5., edge=1):
+    seg = np.ascontiguousarray(seg_binary, dtype=np.int8)
+    s, c = ray_angles(float(angle_step))
+    out = np.empty(len(s), dtype=np.float32)
+    lib().oracle_ray_features2d(_p(seg, C.c_int8), seg.shape[0], seg.shape[1], int(position[0]), int(position[1]),
+                                _p(s, C.c_float), _p(c, C.c_float), len(s), int(edge), _p(out, C.c_float))
+    return out

@@ -115,7 +115,8 @@ int oracle_ray_features2d(const int8_t* seg, int H, int W, int pr, int pc, const
             int8_t actual = seg[(long)((int)roundf(pos0)) * W + (int)roundf(pos1)];
             if ((edge == 1 && actual) || (edge == -1 && last && !actual)) {
                 float dx = pos0 - (float)pr, dy = pos1 - (float)pc;
-                ray_dist[i] = sqrtf(dx * dx + dy * dy);
+                /* the products and the sum are C floats, np.sqrt then works on the Python float (double), the store rounds to f32 */
+                ray_dist[i] = (float)sqrt((double)(dx * dx + dy * dy));
                 break;
             }
             last = actual;

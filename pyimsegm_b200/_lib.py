@@ -45,6 +45,10 @@ SIGNATURES = {
     'isb_lm_workspace_bytes': (_sz, [_i, _i, _i, _i]),
     'isb_lm_texture': (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, C.POINTER(_d), _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _sz, _vp]),
     'isb_fill_i32': (_i, [_vp, _ll, _i, _vp]),
+    'isb_gray_stats_workspace_bytes': (_sz, [_i]),
+    'isb_gray_stats': (_i, [_vp, _i, _vp, _ll, _i, _i, _vp, _i, _i, _vp, _sz, _vp]),
+    'isb_label_hist_2d': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    'isb_ray_features_2d': (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp]),
     'isb_gather': (_i, [_vp, _ll, _vp, _vp, _i, _vp, _vp, _vp]),
 }
 

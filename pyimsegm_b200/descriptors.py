@@ -160,6 +160,85 @@ def numpy_img2d_color_median(img, seg):
     return medians
 
 
+def _device_gray_stats(img, seg, flags):
+    import ctypes as C
+    from . import _lib
+    img, seg = _device_dtype(img), np.asarray(seg)
+    _check_gray_image_segm(img, seg)
+    eng = get_engine()
+    nb = int(seg.max()) + 1
+    d_img = eng.to_device(img, 'image_gray')
+    d_seg = eng.to_device(seg.astype(np.int32, copy=False), 'seg_in')
+    bits = sum(FLAG_BITS[f] for f in flags)
+    feat = eng.buf('feat_gray', (nb, len(flags)), eng.torch.float64)
+    wsb = eng.lib.isb_gray_stats_workspace_bytes(nb)
+    ws = eng.buf('ws_gray', (wsb,), eng.torch.uint8)
+    _lib.check(eng.lib.isb_gray_stats(_lib.ptr(d_img), _lib.DTYPE_CODES[str(img.dtype)], _lib.ptr(d_seg), C.c_longlong(img.size), nb, bits,
+                                      _lib.ptr(feat), len(flags), 0, _lib.ptr(ws), C.c_size_t(wsb), _lib.stream_ptr()))
+    return eng.to_host(feat).copy()
+
+
+def cython_img3d_gray_mean(img, seg):
+    """ mean intensity per segment of a gray volume (reference descriptors.py:458-487) """
+    return _device_gray_stats(img, seg, ('mean', ))[:, 0]
+
+
+def cython_img3d_gray_energy(img, seg):
+    """ mean squared intensity per segment of a gray volume (reference descriptors.py:490-515) """
+    return _device_gray_stats(img, seg, ('energy', ))[:, 0]
+
+
+def cython_img3d_gray_std(img, seg, mean=None):
+    """ intensity STD per segment of a gray volume, two-pass about the f32 mean (reference descriptors.py:518-551) """
+    return _device_gray_stats(img, seg, ('std', ))[:, 0]
+
+
+def cython_label_hist_seg2d(segm_select, struc_elem, nb_labels):
+    """ histogram of the labels under a structuring element (reference descriptors.py:1479-1498) """
+    import ctypes as C
+    from . import _lib
+    segm_select, struc_elem = np.array(segm_select, dtype=float), np.asarray(struc_elem)
+    if segm_select.shape != struc_elem.shape:
+        raise ValueError('segm. %r and mask %r sizes do not match' % (segm_select.shape, struc_elem.shape))
+    segm_select[np.isnan(segm_select)] = -1
+    eng = get_engine()
+    d_a = eng.to_device(segm_select.astype(np.int16), 'hist_segm')
+    d_b = eng.to_device(struc_elem.astype(np.int16), 'hist_selem')
+    hist = eng.buf('hist_out', (int(nb_labels),), eng.torch.int32)
+    _lib.check(eng.lib.isb_label_hist_2d(_lib.ptr(d_a), _lib.ptr(d_b), segm_select.shape[0], segm_select.shape[1], int(nb_labels),
+                                         _lib.ptr(hist), _lib.stream_ptr()))
+    return eng.to_host(hist).astype(float)
+
+
+def ray_angle_tables(angle_step):
+    """(sin, cos) float32 tables of the ray directions exactly as features_cython.pyx:247-268 forms them"""
+    angles = np.arange(0, 360, angle_step, dtype=np.float32)
+    rads = [float(np.float32(np.deg2rad(a))) for a in angles]
+    return np.array([np.sin(r) for r in rads], dtype=np.float32), np.array([np.cos(r) for r in rads], dtype=np.float32)
+
+
+def cython_ray_features_seg2d(seg_binary, position, angle_step=5., edge='up'):
+    """ Ray features: distance from ``position`` to the first boundary along rays every ``angle_step`` degrees
+    (reference descriptors.py:1628-1660).  ``position`` may also be an [n, 2] array: all positions run in one launch.
+
+    :return ndarray: ray distances, float32 [n_angles] (or [n, n_angles])
+    """
+    import ctypes as C
+    from . import _lib
+    edge_int = {'down': -1, 'up': 1}[edge]
+    seg = np.array(seg_binary, dtype=np.int8)
+    pos = np.atleast_2d(np.array(position, dtype=np.int32))
+    sin_a, cos_a = ray_angle_tables(float(angle_step))
+    eng = get_engine()
+    d_seg, d_pos = eng.to_device(seg, 'ray_seg'), eng.to_device(pos, 'ray_pos')
+    d_s, d_c = eng.to_device(sin_a, 'ray_sin'), eng.to_device(cos_a, 'ray_cos')
+    out = eng.buf('ray_out', (len(pos), len(sin_a)), eng.torch.float32)
+    _lib.check(eng.lib.isb_ray_features_2d(_lib.ptr(d_seg), seg.shape[0], seg.shape[1], _lib.ptr(d_pos), len(pos), _lib.ptr(d_s), _lib.ptr(d_c),
+                                           len(sin_a), edge_int, _lib.ptr(out), _lib.stream_ptr()))
+    res = eng.to_host(out).copy()
+    return res[0] if np.ndim(position) == 1 else res
+
+
 def compute_image2d_color_statistic(image, segm, feature_flags=NAMES_FEATURE_FLAGS, color_name='color'):
     """ statistics of a colour image over the segments; columns are statistic-major, channel-minor
     (reference descriptors.py:787-863)

@@ -277,3 +277,46 @@ def test_config1_reference_cpu_case(oracle):
     segm2, _ = pl.segment_color2d_slic_features_model_graphcut(img, model, feats, sp_size=25, sp_regul=0.2)
     segm_o, _, _, _ = oracle.segment_with_model(img, model.predict_proba, ('mean',), 25, 0.2, 1., 'model')
     assert np.array_equal(segm, segm2) and np.array_equal(segm2, segm_o)
+
+
+def test_remaining_native_functions(oracle):
+    """gray 3-D statistics, label histogram and ray features of imsegm/features_cython.pyx (:144-282): doctest goldens of
+    imsegm/descriptors.py:470-478, :1479-1485, :1641-1653, the oracle, and the reference module compiled unchanged.
+    Ray distances: 1e-5 relative against the compiled reference (it is built with -ffast-math, its last float ulp is
+    compiler dependent); exact against the oracle and against the integer goldens."""
+    from pyimsegm_b200 import descriptors as ds
+    image = np.zeros((2, 3, 8))
+    image[0, :, 2:6] = 1
+    image[1, :, 3:7] = 3
+    segm = np.array([[[0, 0, 0, 0, 1, 1, 1, 1]] * 3, [[2, 2, 2, 2, 3, 3, 3, 3]] * 3])
+    np.testing.assert_allclose(ds.cython_img3d_gray_mean(image, segm), [0.5, 0.5, 0.75, 2.25], rtol=1e-12)
+    rng = np.random.RandomState(0)
+    vol = rng.random_sample((5, 40, 50)).astype(np.float32)
+    seg = (np.arange(5)[:, None, None] * 20 + np.arange(40)[None, :, None] // 10 * 5 + np.arange(50)[None, None, :] // 10)
+    for mode, fn in ((0, ds.cython_img3d_gray_mean), (1, ds.cython_img3d_gray_energy)):
+        np.testing.assert_allclose(fn(vol, seg), oracle.gray3d_stat(vol, seg, mode), rtol=1e-6)
+    np.testing.assert_allclose(ds.cython_img3d_gray_std(vol, seg), np.sqrt(oracle.gray3d_stat(vol, seg, 2, oracle.gray3d_stat(vol, seg, 0))), rtol=1e-6)
+    s = np.array([[0, 1, 2], [1, 1, -1], [2, 2, 2]])
+    assert ds.cython_label_hist_seg2d(s, np.ones((3, 3)), 3).tolist() == [1.0, 3.0, 4.0]
+    big = rng.randint(-1, 6, (64, 80))
+    mask = (rng.rand(64, 80) < 0.5).astype(int)
+    assert ds.cython_label_hist_seg2d(big, mask, 6).tolist() == oracle.label_hist2d(big, mask, 6).astype(float).tolist()
+    seg_empty = np.zeros((100, 150), dtype=bool)
+    assert ds.cython_ray_features_seg2d(seg_empty, (50, 75), 90).tolist() == [-1., -1., -1., -1.]
+    seg = np.ones((100, 150), dtype=bool)
+    yy, xx = np.mgrid[:100, :150]
+    seg[(yy - 50) ** 2 + (xx - 75) ** 2 < 40 ** 2] = False              # skimage.draw.disk((50, 75), 40)
+    assert ds.cython_ray_features_seg2d(seg, (50, 75), 45).astype(int).tolist() == [40, 41, 40, 41, 40, 41, 40, 41]
+    assert ds.cython_ray_features_seg2d(seg, (60, 40), 30).astype(int).tolist() == [74, 55, 28, 10, 5, 4, 4, 5, 9, 30, 57, 75]
+    assert ds.cython_ray_features_seg2d(seg, (40, 60), 20).astype(int).tolist() == \
+        [54, 57, 58, 55, 50, 43, 38, 31, 26, 24, 22, 22, 23, 26, 29, 34, 41, 48]
+    fc = oracle.ref_features_cython()
+    noise = rng.rand(40, 60) < 0.08
+    pos = np.stack([rng.randint(0, 40, 25), rng.randint(0, 60, 25)], 1)
+    for edge, e in (('up', 1), ('down', -1)):
+        got = ds.cython_ray_features_seg2d(noise, pos, 7.5, edge)
+        for p, g in zip(pos, got):
+            assert np.array_equal(g, oracle.ray_features2d(noise, p, 7.5, e))
+            if fc is not None:
+                ref = np.array(fc.computeRayFeaturesBinary2d(noise.astype(np.int8), np.array(p, dtype=np.int32), 7.5, e))
+                np.testing.assert_allclose(g, ref, rtol=1e-5)
