@@ -23,8 +23,8 @@
  * (superpixels.py:32-40) and the real library cannot be run here.  Two deliberate definitions make the
  * result reproducible bit-for-bit on any IEEE machine (CPU or GPU):
  *   - pow(t, 2.4) and cbrt(t) are computed by det_pow24()/det_cbrt() below: fixed sequences of
- *     + - * / on doubles (Newton iterations from an integer-bit initial guess).  They agree with libm
- *     to a few ulp; libm itself differs between platforms at that level.
+ *     + - * on doubles (division-free Newton iterations on the inverse root from an integer-bit seed).
+ *     They agree with libm to a few ulp; libm itself differs between platforms at that level.
  *   - the 3x3 colour matrix product is evaluated as (r*m0 + g*m1) + b*m2 without fused multiply-add.
  *   - a cluster that loses all its pixels gets a 0/0 centroid in the original; on x86 the NaN window
  *     bounds cast to INT64_MIN and the cluster is never assigned again.  Here: count==0 => dead forever.
@@ -39,34 +39,50 @@
 
 /* ---------- deterministic math (pure IEEE + - * /) ---------- */
 
-static double det_cbrt(double x) /* x > 0, moderate range */
+static double det_cbrt(double x) /* x in (0.008, 1.3) */
 {
+    /* division-free: Newton on y = x^(-1/3)  (y <- y (4 - x y^3) / 3, seed from the exponent bits, 3.4 % off),
+     * then cbrt = x y^2 and one correction step c <- c - (c^3 - x) y^2 / 3 */
     union { double d; uint64_t u; } v;
     v.d = x;
-    v.u = v.u / 3u + 0x2A9F7893782DA1CEull; /* exponent/3 initial guess, ~5% */
+    v.u = 0x553EF00000000000ull - v.u / 3u;
     double y = v.d;
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < 4; ++i) {
         double y2 = y * y;
         double y3 = y2 * y;
-        /* Newton: y <- y - (y^3 - x) / (3 y^2) */
-        y = y - (y3 - x) / (3.0 * y2);
+        double t = x * y3;
+        double u = 4.0 - t;
+        y = (y * u) * (1.0 / 3.0);
     }
-    return y;
+    double y2 = y * y;
+    double c = x * y2;
+    double c3 = (c * c) * c;
+    c = c - ((c3 - x) * y2) * (1.0 / 3.0);
+    return c;
 }
 
-static double det_root5(double x) /* x > 0 */
+static double det_root5(double x) /* x in (0.05, 1.1) */
 {
+    /* division-free: Newton on y = x^(-1/5)  (y <- y (6 - x y^5) / 5), then x^(1/5) = x y^4 and one correction step */
     union { double d; uint64_t u; } v;
     v.d = x;
-    v.u = v.u / 5u + 0x3325AE2B9DCF9A9Aull; /* (4/5)*bits(1.0) rounded; ~10% guess */
+    v.u = 0x4CB8A99999999800ull - v.u / 5u;
     double y = v.d;
-    for (int i = 0; i < 7; ++i) {
+    for (int i = 0; i < 4; ++i) {
         double y2 = y * y;
         double y4 = y2 * y2;
-        /* Newton on y^5 - x: y <- (4 y + x / y^4) / 5 */
-        y = (4.0 * y + x / y4) / 5.0;
+        double y5 = y4 * y;
+        double t = x * y5;
+        double u = 6.0 - t;
+        y = (y * u) * 0.2;
     }
-    return y;
+    double y2 = y * y;
+    double y4 = y2 * y2;
+    double r = x * y4;
+    double r2 = r * r;
+    double r5 = (r2 * r2) * r;
+    r = r - ((r5 - x) * y4) * 0.2;
+    return r;
 }
 
 static double det_pow24(double t) /* t^2.4 = t^2 * (t^(1/5))^2 */

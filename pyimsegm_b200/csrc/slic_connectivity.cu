@@ -270,18 +270,22 @@ __global__ void k_small_adjacent(int H, int W, const int* __restrict__ comp, con
     vis[C] = 1;
     int n = 1, v = 0;
     while (v < n && n < max_size) {
-        int cp = q[v];
-        int cy = cp / W, cx = cp - cy * W;
-        const int nx[4] = { cx + 1, cx - 1, cx, cx };
-        const int ny[4] = { cy, cy, cy + 1, cy - 1 };
+        const int cp = q[v];
+        const int cy = cp / W, cx = cp - cy * W;
+        // the four neighbours in the original's order (+x, -x, +y, -y); their component ids are fetched together
+        // (independent loads) before the order-dependent bookkeeping
+        const int np4[4] = { cx + 1 < W ? cp + 1 : -1, cx > 0 ? cp - 1 : -1, cy + 1 < H ? cp + W : -1, cy > 0 ? cp - W : -1 };
+        int r4[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) r4[d] = np4[d] >= 0 ? dec(comp[np4[d]]) : INT_MAX;
+#pragma unroll
         for (int d = 0; d < 4; ++d) {
-            if (nx[d] < 0 || nx[d] >= W || ny[d] < 0 || ny[d] >= H) continue;
-            int np_ = ny[d] * W + nx[d];
-            int r = dec(comp[np_]);
+            if (np4[d] < 0) continue;
+            const int r = r4[d];
             if (r == C) {
-                if (!vis[np_]) {
-                    vis[np_] = 1;
-                    q[n++] = np_;
+                if (!vis[np4[d]]) {
+                    vis[np4[d]] = 1;
+                    q[n++] = np4[d];
                     if (n >= max_size) break;
                 }
             } else if (r < C) {

@@ -70,10 +70,14 @@ __device__ __forceinline__ int4 make_window(double cy, double cx, int step_y, in
 // first == 1: take centres from the seed grid (colour part 0);  else divide the update sums by the counts.
 __global__ void __launch_bounds__(1024) k_finalize_bin(KmState s, const double* seeds_yx, int first)
 {
+    // first == 1: centres from the seed grid; first == 0: divide the update sums (legacy path); first == 2: k_update already
+    // wrote centroids, windows, bin_of and counted the bins -> only scan + fill here
     const int nbins = s.nby * s.nbx;
-    for (int b = threadIdx.x; b < nbins; b += blockDim.x) s.bin_fill[b] = 0;
-    __syncthreads();
-    for (int k = threadIdx.x; k < s.n; k += blockDim.x) {
+    if (first != 2) {
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x) s.bin_fill[b] = 0;
+        __syncthreads();
+    }
+    for (int k = threadIdx.x; k < s.n && first != 2; k += blockDim.x) {
         int4 w = make_int4(0, 0, 0, 0);
         int bin = -1;
         bool dead = false;
@@ -149,6 +153,8 @@ __global__ void __launch_bounds__(1024) k_finalize_bin(KmState s, const double* 
         c.y0 = w.x; c.y1 = w.y; c.x0 = w.z; c.x1 = w.w; c.k = k; c.pad = 0;
         s.packed[pos] = c;
     }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) s.bin_fill[b] = 0; // k_update counts the next sweep's bins from zero
 }
 
 // non-negative doubles order like their bit patterns: compare on the integer pipe instead of the FP64 pipe
@@ -355,33 +361,62 @@ __global__ void __launch_bounds__(256) k_update(KmState s, const double* __restr
     const size_t HW = (size_t)s.H * s.W;
     double acc = 0.0;
     long long cnt = 0, sy = 0, sx = 0;
-    for (int y = y0; y < y1; ++y) {
-        const size_t rowp = (size_t)y * s.W;
-        for (int xb = x0; xb < x1; xb += 32) {
-            const int x = xb + lane;
-            const bool m = (x < x1) && (labels[rowp + x] == k);
-            const unsigned mask = __ballot_sync(0xffffffffu, m);
-            if (!mask) continue;
-            const int nm = __popc(mask);
-            if (m) {
-                int pos = __popc(mask & ((1u << lane) - 1u));
-                buf[wl][0][pos] = lab[rowp + x];
-                buf[wl][1][pos] = lab[HW + rowp + x];
-                buf[wl][2][pos] = lab[2 * HW + rowp + x];
-                sx += x;
-            }
-            cnt += nm;
-            sy += (long long)y * nm;
-            __syncwarp();
-            if (lane < 3)
-                for (int i = 0; i < nm; ++i) acc = __dadd_rn(acc, buf[wl][lane][i]);
-            __syncwarp();
+    // the box is walked in raster order, 32 pixels at a time; the label load of the next chunk is issued before the current
+    // chunk is processed (the loads are the latency that bounds this kernel)
+    const int nchunk = (x1 > x0) ? (x1 - x0 + 31) / 32 : 0;
+    const int total = (y1 > y0) ? (y1 - y0) * nchunk : 0;
+    int y = y0, xb = x0;
+    int lab_next = -1;
+    if (total > 0) { const int x = xb + lane; lab_next = (x < x1) ? labels[(size_t)y * s.W + x] : -1; }
+    for (int it = 0; it < total; ++it) {
+        const int cy_ = y, cxb = xb;
+        const int lab_cur = lab_next;
+        xb += 32;
+        if (xb >= x1) { xb = x0; ++y; }
+        if (it + 1 < total) { const int x = xb + lane; lab_next = (x < x1) ? labels[(size_t)y * s.W + x] : -1; }
+        const int x = cxb + lane;
+        const bool m = lab_cur == k;
+        const unsigned mask = __ballot_sync(0xffffffffu, m);
+        if (!mask) continue;
+        const size_t rowp = (size_t)cy_ * s.W;
+        const int nm = __popc(mask);
+        if (m) {
+            int pos = __popc(mask & ((1u << lane) - 1u));
+            buf[wl][0][pos] = lab[rowp + x];
+            buf[wl][1][pos] = lab[HW + rowp + x];
+            buf[wl][2][pos] = lab[2 * HW + rowp + x];
+            sx += x;
         }
+        cnt += nm;
+        sy += (long long)cy_ * nm;
+        __syncwarp();
+        if (lane < 3)
+            for (int i = 0; i < nm; ++i) acc = __dadd_rn(acc, buf[wl][lane][i]);
+        __syncwarp();
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, d);
-    if (lane < 3) s.sums[3 * k + lane] = acc;
-    if (lane == 0) { s.isum[3 * k] = cnt; s.isum[3 * k + 1] = sy; s.isum[3 * k + 2] = sx; }
+    // centroid = sums / count with IEEE divisions (the original divides every feature by the element count), new window,
+    // bin of the new centre; a cluster without pixels is dead for good
+    const double a0 = __shfl_sync(0xffffffffu, acc, 0), a1 = __shfl_sync(0xffffffffu, acc, 1), a2 = __shfl_sync(0xffffffffu, acc, 2);
+    if (lane == 0) {
+        int4 w = make_int4(0, 0, 0, 0);
+        int bin = -1;
+        if (cnt > 0) {
+            const double dn = (double)cnt;
+            const double cy = __ddiv_rn((double)sy, dn), cx = __ddiv_rn((double)sx, dn);
+            s.cy[k] = cy; s.cx[k] = cx;
+            s.c0[k] = __ddiv_rn(a0, dn); s.c1[k] = __ddiv_rn(a1, dn); s.c2[k] = __ddiv_rn(a2, dn);
+            w = make_window(cy, cx, s.step_y, s.step_x, s.H, s.W);
+            const int by = min(max((int)cy / s.B, 0), s.nby - 1), bx = min(max((int)cx / s.B, 0), s.nbx - 1);
+            bin = by * s.nbx + bx;
+            atomicAdd(&s.bin_fill[bin], 1);
+        }
+        s.win[k] = w;
+        s.bin_of[k] = bin;
+        s.obb[k] = make_int4(INT_MAX, -1, INT_MAX, -1);
+        s.isum[3 * k] = cnt;
+    }
 }
 
 __global__ void k_export_centroids(KmState s, double* out)
@@ -396,8 +431,8 @@ static size_t carve(KmState& s, void* ws, size_t bytes, int H, int W, int n, int
 {
     WsCarver c(ws, bytes);
     s.n = n; s.H = H; s.W = W; s.step_y = step_y; s.step_x = step_x;
-    s.B = step_y > step_x ? step_y : step_x;
-    if (s.B < 8) s.B = 8;
+    s.B = 2 * (step_y > step_x ? step_y : step_x); // bin edge: coarse enough that the per-sweep scan over the bins is short
+    if (s.B < 16) s.B = 16;
     s.nby = (H + s.B - 1) / s.B; s.nbx = (W + s.B - 1) / s.B;
     s.cy = c.take<double>(n); s.cx = c.take<double>(n);
     s.c0 = c.take<double>(n); s.c1 = c.take<double>(n); s.c2 = c.take<double>(n);
@@ -439,7 +474,7 @@ extern "C" int isb_slic_kmeans(const double* lab_planar, int H, int W, const dou
         ISB_LAUNCH_CHECK();
         { ProfScope p(ISB_PROF_UPDATE, st); k_update<<<(n_seeds + 7) / 8, 256, 0, st>>>(s, lab_planar, labels); }
         ISB_LAUNCH_CHECK();
-        { ProfScope p(ISB_PROF_FINALIZE, st); k_finalize_bin<<<1, 1024, 0, st>>>(s, seeds_yx, 0); }
+        { ProfScope p(ISB_PROF_FINALIZE, st); k_finalize_bin<<<1, 1024, 0, st>>>(s, seeds_yx, 2); }
         ISB_LAUNCH_CHECK();
     }
     if (centroids) {

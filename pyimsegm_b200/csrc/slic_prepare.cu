@@ -18,33 +18,47 @@ __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a,
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 
-// cube root by Newton from an exponent/3 bit guess: fixed sequence of IEEE ops (DESIGN.md "deterministic math")
+// cube root, division-free: Newton on y = x^(-1/3) from an exponent-bit seed, then x y^2 and one correction step.
+// A fixed sequence of IEEE mul / sub -- the same sequence as oracle/slic_oracle.c (DESIGN.md "deliberate definitions").
 __device__ __forceinline__ double det_cbrt(double x)
 {
-    unsigned long long u = (unsigned long long)__double_as_longlong(x);
-    u = u / 3ull + 0x2A9F7893782DA1CEull;
+    unsigned long long u = 0x553EF00000000000ull - (unsigned long long)__double_as_longlong(x) / 3ull;
     double y = __longlong_as_double((long long)u);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        double y2 = dmul(y, y);
-        double y3 = dmul(y2, y);
-        y = dsub(y, ddiv(dsub(y3, x), dmul(3.0, y2)));
+    for (int i = 0; i < 4; ++i) {
+        const double y2 = dmul(y, y);
+        const double y3 = dmul(y2, y);
+        const double t = dmul(x, y3);
+        const double w = dsub(4.0, t);
+        y = dmul(dmul(y, w), 1.0 / 3.0);
     }
-    return y;
+    const double y2 = dmul(y, y);
+    double c = dmul(x, y2);
+    const double c3 = dmul(dmul(c, c), c);
+    c = dsub(c, dmul(dmul(dsub(c3, x), y2), 1.0 / 3.0));
+    return c;
 }
 
 __device__ __forceinline__ double det_root5(double x)
 {
-    unsigned long long u = (unsigned long long)__double_as_longlong(x);
-    u = u / 5ull + 0x3325AE2B9DCF9A9Aull;
+    unsigned long long u = 0x4CB8A99999999800ull - (unsigned long long)__double_as_longlong(x) / 5ull;
     double y = __longlong_as_double((long long)u);
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
-        double y2 = dmul(y, y);
-        double y4 = dmul(y2, y2);
-        y = ddiv(dadd(dmul(4.0, y), ddiv(x, y4)), 5.0);
+    for (int i = 0; i < 4; ++i) {
+        const double y2 = dmul(y, y);
+        const double y4 = dmul(y2, y2);
+        const double y5 = dmul(y4, y);
+        const double t = dmul(x, y5);
+        const double w = dsub(6.0, t);
+        y = dmul(dmul(y, w), 0.2);
     }
-    return y;
+    const double y2 = dmul(y, y);
+    const double y4 = dmul(y2, y2);
+    double r = dmul(x, y4);
+    const double r2 = dmul(r, r);
+    const double r5 = dmul(dmul(r2, r2), r);
+    r = dsub(r, dmul(dmul(dsub(r5, x), y4), 0.2));
+    return r;
 }
 
 __device__ __forceinline__ double det_pow24(double t)
