@@ -94,7 +94,7 @@ __device__ __forceinline__ double log_prob_all(const double* x, int D, int K, co
             for (int i = 0; i <= j; ++i) y += (x[i] - m[i]) * U[i * D + j];
             q += y * y;
         }
-        double lp = -0.5 * (D * 1.8378770664093453 + q) + logdet[k] + log(wts[k]);
+        double lp = -0.5 * (D * 1.8378770664093453 + q) + logdet[k]; // logdet[k] already holds log|prec_chol_k| + log w_k
         lw[k] = lp;
         mx = fmax(mx, lp);
     }
@@ -273,23 +273,39 @@ __global__ void __launch_bounds__(GT) k_gmm_fit(int N_in, const int* n_dev, int 
                 if (lab[n] != bk) { lab[n] = bk; changed = 1; }
             }
             changed = __syncthreads_or(changed);
-            // new centres
+            // new centres: count and coordinate sums of every cluster in ONE quantity-parallel pass over sample slices
+            // (quantity q = (k, j): j == 0 the count, j >= 1 the sum of coordinate j-1)
+            const int Q = K * (1 + D);                 // <= 8 * 17 = 136 <= GT
+            const int S = max(1, GT / Q);
+            {
+                const int q = threadIdx.x % Q, sl = threadIdx.x / Q;
+                double a = 0;
+                if (sl < S) {
+                    const int k = q / (1 + D), j = q % (1 + D);
+                    for (int n = sl; n < N; n += S)
+                        if (lab[n] == k) a += j == 0 ? 1.0 : xs[(size_t)n * D + j - 1];
+                }
+                s_part[threadIdx.x] = a;
+            }
+            __syncthreads();
+            __shared__ double s_tot[KMAX * (1 + DMAX)];
+            if (threadIdx.x < Q) {
+                double t = 0;
+                for (int s2 = 0; s2 < S; ++s2) t += s_part[s2 * Q + threadIdx.x];
+                s_tot[threadIdx.x] = t;
+            }
+            __syncthreads();
             double shift = 0;
             for (int k = 0; k < K; ++k) {
-                double cnt = 0;
-                for (int n = threadIdx.x; n < N; n += GT) cnt += (lab[n] == k);
-                cnt = block_sum_d(cnt, s_red);
-                for (int d = 0; d < D; ++d) {
-                    double s = 0;
-                    for (int n = threadIdx.x; n < N; n += GT) if (lab[n] == k) s += xs[(size_t)n * D + d];
-                    s = block_sum_d(s, s_red);
-                    if (cnt > 0) {
-                        double nc = s / cnt, t = nc - s_cent[k * D + d];
-                        shift += t * t;
-                        __syncthreads();
-                        if (threadIdx.x == 0) s_cent[k * D + d] = nc;
-                    }
-                }
+                const double cnt = s_tot[k * (1 + D)];
+                if (cnt > 0)
+                    for (int d = 0; d < D; ++d) { const double t = s_tot[k * (1 + D) + 1 + d] / cnt - s_cent[k * D + d]; shift += t * t; }
+            }
+            __syncthreads();
+            if (threadIdx.x < K * D) {
+                const int k = threadIdx.x / D, d = threadIdx.x % D;
+                const double cnt = s_tot[k * (1 + D)];
+                if (cnt > 0) s_cent[threadIdx.x] = s_tot[k * (1 + D) + 1 + d] / cnt;
             }
             __syncthreads();
             if (!changed || shift <= 1e-4) break;
@@ -309,7 +325,7 @@ __global__ void __launch_bounds__(GT) k_gmm_fit(int N_in, const int* n_dev, int 
             if (threadIdx.x < K) {
                 double ld = 0;
                 for (int j = 0; j < D; ++j) ld += log(pc[(size_t)threadIdx.x * D * D + j * D + j]);
-                s_logdet[threadIdx.x] = ld;
+                s_logdet[threadIdx.x] = ld + log(wts[threadIdx.x]);
             }
             __syncthreads();
             double acc = 0;
@@ -352,7 +368,7 @@ __global__ void __launch_bounds__(256) k_gmm_predict(int N_in, const int* n_dev,
     if (threadIdx.x < K) {
         double ld = 0;
         for (int j = 0; j < D; ++j) ld += log(pc[(size_t)threadIdx.x * D * D + j * D + j]);
-        s_logdet[threadIdx.x] = ld;
+        s_logdet[threadIdx.x] = ld + log(wts[threadIdx.x]);
     }
     __syncthreads();
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {

@@ -29,10 +29,10 @@ struct ConnWs {
     int* row_cnt;  // [H + 1]
     int* ctr;      // [8] counters: 0 n_oversize, 1 n_small, 2 queue cursor
     int4* bbox;    // [n_oversize_max]
-    unsigned char* vis; // [HW]
 };
 
-__device__ __forceinline__ int dec(int c) { return c < 0 ? ~c : c; }
+constexpr int VISBIT = 1 << 30; // 'visited by the small-piece BFS' flag kept inside comp[] (pixel indices stay below 2^30)
+__device__ __forceinline__ int dec(int c) { return (c < 0 ? ~c : c) & ~VISBIT; }
 
 __device__ __forceinline__ int find_root(const int* parent, int i)
 {
@@ -258,8 +258,8 @@ __global__ void __launch_bounds__(256) k_row_assign_labels(int H, int W, const i
 }
 
 // one thread per small piece: replay its BFS, remember the last foreign earlier-labelled neighbour piece
-__global__ void k_small_adjacent(int H, int W, const int* __restrict__ comp, const int* __restrict__ size, int max_size,
-                                 const int* __restrict__ list, int* ctr, int* aux, int* queue, unsigned char* vis)
+__global__ void k_small_adjacent(int H, int W, int* comp, const int* __restrict__ size, int max_size,
+                                 const int* __restrict__ list, int* ctr, int* aux, int* queue)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ctr[1]) return;
@@ -267,24 +267,27 @@ __global__ void k_small_adjacent(int H, int W, const int* __restrict__ comp, con
     int* q = queue + atomicAdd(&ctr[2], size[C]);
     int adjacent = -1;
     q[0] = C;
-    vis[C] = 1;
+    // the visited flag lives in comp[] itself (only this thread writes the pixels of its own piece; every reader masks the
+    // flag with dec()), so one round of four independent loads per BFS step is all the memory latency there is
+    comp[C] = (comp[C] < 0 ? ~(dec(comp[C]) | VISBIT) : (comp[C] | VISBIT));
     int n = 1, v = 0;
     while (v < n && n < max_size) {
         const int cp = q[v];
         const int cy = cp / W, cx = cp - cy * W;
-        // the four neighbours in the original's order (+x, -x, +y, -y); their component ids are fetched together
-        // (independent loads) before the order-dependent bookkeeping
+        // the four neighbours in the original's order (+x, -x, +y, -y)
         const int np4[4] = { cx + 1 < W ? cp + 1 : -1, cx > 0 ? cp - 1 : -1, cy + 1 < H ? cp + W : -1, cy > 0 ? cp - W : -1 };
-        int r4[4];
+        int raw4[4];
 #pragma unroll
-        for (int d = 0; d < 4; ++d) r4[d] = np4[d] >= 0 ? dec(comp[np4[d]]) : INT_MAX;
+        for (int d = 0; d < 4; ++d) raw4[d] = np4[d] >= 0 ? comp[np4[d]] : 0;
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
             if (np4[d] < 0) continue;
-            const int r = r4[d];
+            const int raw = raw4[d];
+            const int r = dec(raw);
             if (r == C) {
-                if (!vis[np4[d]]) {
-                    vis[np4[d]] = 1;
+                const bool seen = ((raw < 0 ? ~raw : raw) & VISBIT) != 0; // the four neighbours of one pixel are distinct
+                if (!seen) {
+                    comp[np4[d]] = raw < 0 ? ~((~raw) | VISBIT) : (raw | VISBIT);
                     q[n++] = np4[d];
                     if (n >= max_size) break;
                 }
@@ -318,7 +321,6 @@ static size_t carve(ConnWs& w, void* ws, size_t bytes, int H, int W)
     w.row_cnt = c.take<int>((size_t)H + 1);
     w.ctr = c.take<int>(8);
     w.bbox = c.take<int4>(n / 16 + 16);
-    w.vis = c.take<unsigned char>(n);
     return isb_align(c.off);
 }
 
@@ -340,7 +342,7 @@ extern "C" int isb_enforce_connectivity(const int32_t* labels, int H, int W, int
                                         int32_t* n_labels_out, void* ws, size_t ws_bytes, isb_stream_t stream)
 {
     ISB_REQUIRE(labels && out && n_labels_out && ws, "null pointer");
-    ISB_REQUIRE(H > 0 && W > 0 && (long long)H * W < 2147483647LL, "bad image size");
+    ISB_REQUIRE(H > 0 && W > 0 && (long long)H * W < (1LL << 30), "bad image size (at most 2^30 pixels)");
     if (max_size < 1) max_size = 1;
     ISB_REQUIRE(max_size >= 16, "max_size < 16 is not supported on the device path (oversize table bound)");
     ConnWs w;
@@ -352,7 +354,6 @@ extern "C" int isb_enforce_connectivity(const int32_t* labels, int H, int W, int
     const int nb = (n + 255) / 256;
     ISB_CUDA_CHECK(cudaMemsetAsync(w.size, 0, sizeof(int) * (size_t)n, st));
     ISB_CUDA_CHECK(cudaMemsetAsync(w.ctr, 0, sizeof(int) * 8, st));
-    ISB_CUDA_CHECK(cudaMemsetAsync(w.vis, 0, (size_t)n, st));
     k_row_runs<<<H, 256, 0, st>>>(labels, H, W, w.comp);
     ISB_LAUNCH_CHECK();
     k_merge_vertical<<<nb, 256, 0, st>>>(labels, H, W, w.comp);
@@ -378,7 +379,7 @@ extern "C" int isb_enforce_connectivity(const int32_t* labels, int H, int W, int
     k_row_assign_labels<<<H, 256, 0, st>>>(H, W, comp, w.size, min_size, w.row_cnt, aux, w.list, w.ctr);
     ISB_LAUNCH_CHECK();
     // upper bound on the number of small roots is n; launch enough threads, the kernel reads the real count
-    k_small_adjacent<<<nb, 256, 0, st>>>(H, W, comp, w.size, max_size, w.list, w.ctr, aux, w.queue, w.vis);
+    k_small_adjacent<<<nb, 256, 0, st>>>(H, W, comp, w.size, max_size, w.list, w.ctr, aux, w.queue);
     ISB_LAUNCH_CHECK();
     k_write_labels<<<nb, 256, 0, st>>>(n, comp, w.size, min_size, aux, out);
     ISB_LAUNCH_CHECK();
