@@ -146,7 +146,10 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    workers = min(64, max(1, int(0.6 * cores)))  # the reference's NB_WORKERS rule, capped to bound host memory
+    # the reference's own rule is NB_WORKERS = 0.6 * cpu_count (pipelines.py:43); on the 128-CPU host of the B200 box the path
+    # stops scaling at ~16 processes (measured: 1 -> 0.86, 8 -> 7.9, 16 -> 12.0, 32 -> 10.1, 64 -> 6.8 MPix/s; memory bound),
+    # so 16 workers is the reference's best case and keeps a step at ~6 s
+    workers = min(16, max(1, int(0.6 * cores)))
     n_img = workers  # one bounded sample per step: `workers` images through the process pool
     for _ in range(args.warmup):
         cpu_reference_throughput(min(n_img, 2), min(workers, 2))
