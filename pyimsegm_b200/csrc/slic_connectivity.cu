@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(1024) k_scan_rows(int H, int* row_cnt, int* n_
         if (threadIdx.x == 1023) s_carry = carry + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) { row_cnt[H] = s_carry; *n_labels_out = s_carry; }
+    // when no component reaches min_size everything is merged into label 0: the map still holds one label
+    if (threadIdx.x == 0) { row_cnt[H] = s_carry; *n_labels_out = s_carry > 0 ? s_carry : 1; }
 }
 
 __global__ void __launch_bounds__(256) k_row_assign_labels(int H, int W, const int* __restrict__ comp, const int* __restrict__ size,

@@ -320,3 +320,42 @@ def test_remaining_native_functions(oracle):
             if fc is not None:
                 ref = np.array(fc.computeRayFeaturesBinary2d(noise.astype(np.int8), np.array(p, dtype=np.int32), 7.5, e))
                 np.testing.assert_allclose(g, ref, rtol=1e-5)
+
+
+@pytest.mark.parametrize('sp_size,regul,shape', [(4, 0.3, (96, 128)), (5, 0.15, (77, 101)), (60, 0.2, (200, 260)), (9, 0.5, (33, 47))])
+def test_slic_extreme_superpixel_sizes(oracle, sp_size, regul, shape):
+    """tiny superpixels overflow the per-tile candidate list (resumable multi-round scan), huge ones span many tiles"""
+    img, _ = synth_regions(shape[0], shape[1], seed=sp_size, cell=16)
+    got, want = _slic_both(oracle, img, sp_size, regul)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize('min_f,max_f', [(0.05, 0.15), (0.3, 0.6), (1.5, 4.0)])
+def test_connectivity_oversize_and_merge_replay(oracle, eng, min_f, max_f):
+    """small max_size forces the truncated-BFS split of oversize components, large min_size forces long merge chains"""
+    import torch
+    from pyimsegm_b200.superpixels import slic_params
+    img, _ = synth_regions(160, 208, seed=21, noise=0.12)
+    n_seg, compact = slic_params(img.shape[:2], 14, 0.25)
+    d_img = torch.from_numpy(img).cuda()
+    labels, n_lab = eng.slic(d_img, n_seg, compact, sigma=1.0, min_size_factor=min_f, max_size_factor=max_f)
+    got = labels.cpu().numpy()
+    lo, hi = img.min(), img.max()
+    want = oracle.slic((img - lo) / (hi - lo), n_seg, compact, sigma=1, min_size_factor=min_f, max_size_factor=max_f)
+    assert np.array_equal(got, want) and int(n_lab.item()) == want.max() + 1
+
+
+def test_degenerate_inputs_do_not_hang():
+    from pyimsegm_b200 import pipelines as pl
+    from pyimsegm_b200 import superpixels as sp
+    tiny = np.random.RandomState(0).random_sample((9, 11, 3))
+    seg = sp.segment_slic_img2d(tiny, 3, 0.3)
+    assert seg.shape == (9, 11) and seg.min() == 0
+    with pytest.raises(ValueError):
+        sp.segment_slic_img2d(tiny, 50, 0.3)                    # superpixel larger than the image
+    const = np.full((40, 50, 3), 0.5)
+    seg = sp.segment_slic_img2d(const, 10, 0.2)                 # 0/0 in the min-max rescale: NaN colours, like the reference
+    assert seg.shape == (40, 50)
+    two = np.zeros((64, 64, 3)); two[:, 32:] = 1.0              # only two distinct values, flat regions tie everywhere
+    segm, soft = pl.pipe_color2d_slic_features_model_graphcut(two, 2, {'color': ['mean']}, sp_size=8)
+    assert len(np.unique(segm)) == 2 and (segm[:, :30] == segm[0, 0]).all() and (segm[:, 34:] == segm[0, -1]).all()
