@@ -105,7 +105,39 @@ __global__ void k_ray_features(const signed char* __restrict__ seg, int H, int W
     out[t] = dist;
 }
 
+// joint histogram of two label maps: hist[a][b] = #{p : slic[p] == a, annot[p] == b}; a thread walks a short column strip so
+// that runs of equal (a, b) cost one atomic
+__global__ void __launch_bounds__(256) k_region_label_hist(const int* __restrict__ slic, const int* __restrict__ annot, int H, int W, int nb_annot,
+                                                           unsigned* hist)
+{
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (x >= W) return;
+    const int y0 = blockIdx.y * GSTRIP, y1 = min(y0 + GSTRIP, H);
+    int ca = -1, cb = -1;
+    unsigned run = 0;
+    for (int y = y0; y <= y1; ++y) {
+        int a = -1, b = -1;
+        if (y < y1) { a = slic[(size_t)y * W + x]; b = annot[(size_t)y * W + x]; }
+        if (a != ca || b != cb) {
+            if (run) atomicAdd(&hist[(size_t)ca * nb_annot + cb], run);
+            ca = a; cb = b; run = 0;
+        }
+        if (y < y1) ++run;
+    }
+}
+
 } // namespace
+
+extern "C" int isb_region_label_hist(const int32_t* slic, const int32_t* annot, int H, int W, int nb_slic, int nb_annot, uint32_t* hist,
+                                     isb_stream_t stream)
+{
+    ISB_REQUIRE(slic && annot && hist && H > 0 && W > 0 && nb_slic > 0 && nb_annot > 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    ISB_CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)nb_slic * nb_annot, st));
+    k_region_label_hist<<<dim3((W + 255) / 256, (H + GSTRIP - 1) / GSTRIP), 256, 0, st>>>(slic, annot, H, W, nb_annot, hist);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
 
 extern "C" size_t isb_gray_stats_workspace_bytes(int nb) { return isb_align(sizeof(double) * 3 * (size_t)nb) + isb_align(sizeof(long long) * (size_t)nb) + isb_align(sizeof(float) * (size_t)nb) + 1024; }
 

@@ -359,3 +359,43 @@ def test_degenerate_inputs_do_not_hang():
     two = np.zeros((64, 64, 3)); two[:, 32:] = 1.0              # only two distinct values, flat regions tie everywhere
     segm, soft = pl.pipe_color2d_slic_features_model_graphcut(two, 2, {'color': ['mean']}, sp_size=8)
     assert len(np.unique(segm)) == 2 and (segm[:, :30] == segm[0, 0]).all() and (segm[:, 34:] == segm[0, -1]).all()
+
+
+def test_region_label_histograms_reference_doctests():
+    """imsegm/labeling.py:215-228 and :252-265"""
+    from pyimsegm_b200 import labeling
+    slic = np.array([[0] * 3 + [1] * 3 + [2] * 3] * 4 + [[4] * 3 + [5] * 3 + [6] * 3] * 4)
+    segm = np.zeros(slic.shape, dtype=int)
+    segm[4:, 5:] = 2
+    want = [[12, 0, 0], [12, 0, 0], [12, 0, 0], [0, 0, 0], [12, 0, 0], [8, 0, 4], [0, 0, 12]]
+    assert labeling.histogram_regions_labels_counts(slic, segm).tolist() == want
+    norm = labeling.histogram_regions_labels_norm(slic, segm)
+    np.testing.assert_allclose(norm[5], [2 / 3., 0, 1 / 3.])
+    assert norm[3].tolist() == [0, 0, 0] and norm[6].tolist() == [0, 0, 1]
+    rng = np.random.RandomState(0)
+    a, b = rng.randint(0, 300, (257, 300)), rng.randint(0, 5, (257, 300))
+    want = np.zeros((300, 5))
+    np.add.at(want, (a.ravel(), b.ravel()), 1)
+    assert np.array_equal(labeling.histogram_regions_labels_counts(a, b), want)
+    with pytest.raises(ValueError):
+        labeling.histogram_regions_labels_counts(a, b - 1)
+
+
+def test_batch_api_equals_single_image_calls():
+    """segment_images_batch (two streams, overlapped copies) returns exactly what the per-image calls return"""
+    from pyimsegm_b200 import graph_cuts as gc
+    from pyimsegm_b200 import pipelines as pl
+    imgs = [synth_regions(160 + 16 * i, 200, seed=30 + i)[0] for i in range(5)]
+    feats = {'color': ['mean', 'std']}
+    batch = pl.segment_images_batch(imgs, nb_classes=3, dict_features=feats, sp_size=14)
+    for im, (segm, soft) in zip(imgs, batch):
+        s1, p1 = pl.pipe_color2d_slic_features_model_graphcut(im, 3, feats, sp_size=14)
+        assert np.array_equal(segm, s1) and np.array_equal(soft, p1)
+    _, fts = pl.compute_color2d_superpixels_features(imgs[0], feats, sp_size=14)
+    model = gc.estim_class_model(fts, 3)
+    batch = pl.segment_images_batch(imgs, dict_features=feats, sp_size=14, model_pipeline=model)
+    for im, (segm, soft) in zip(imgs, batch):
+        s1, p1 = pl.segment_color2d_slic_features_model_graphcut(im, model, feats, sp_size=14)
+        assert np.array_equal(segm, s1) and np.allclose(soft, p1)
+    with pytest.raises(ValueError):
+        pl.segment_images_batch(imgs, nb_classes=3, model_pipeline=model)
