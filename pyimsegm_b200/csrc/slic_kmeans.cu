@@ -41,13 +41,13 @@ struct KmState {
     double* cy; double* cx; double* c0; double* c1; double* c2;
     int4* win;       // [n] (y0, y1, x0, x1); empty (0,0,0,0) when dead
     int4* obb;       // [n] bbox of the cluster's member pixels (ymin, ymax, xmin, xmax), empty = (INT_MAX, -1, INT_MAX, -1)
-    double* sums;    // [n][3] colour sums of the current update
-    long long* isum; // [n][3] count, sum y, sum x
     int* bin_start;  // [nbins + 1]
     int* bin_fill;   // [nbins]
-    int* bin_items;  // [n]
     int* bin_of;     // [n]
     Cand* packed;    // [n] cluster records in bin order (what k_assign streams)
+    double* packed_maxdc; // [n] SLICO: the maxima in bin order, beside `packed`
+    unsigned long long* maxdc; // [n] SLICO colour-distance maxima as raw double bits (non-negative doubles order like their bits)
+    int slico;
     int n, H, W, step_y, step_x, B, nby, nbx;
     double sw;       // spatial weight 1/step^2
 };
@@ -66,49 +66,25 @@ __device__ __forceinline__ int4 make_window(double cy, double cx, int step_y, in
     return w;
 }
 
-// single CTA: (re)compute centroids + windows, then bin the live clusters by centroid position.
-// first == 1: take centres from the seed grid (colour part 0);  else divide the update sums by the counts.
+// single CTA.  first == 1: centres from the seed grid (colour part 0), windows, bin counts.  Then (always): exclusive scan
+// of the bin counts and the packed, bin-ordered cluster records that k_assign streams.  In the sweeps k_update has already
+// written centroids, windows, bin_of and counted the bins.
 __global__ void __launch_bounds__(1024) k_finalize_bin(KmState s, const double* seeds_yx, int first)
 {
-    // first == 1: centres from the seed grid; first == 0: divide the update sums (legacy path); first == 2: k_update already
-    // wrote centroids, windows, bin_of and counted the bins -> only scan + fill here
     const int nbins = s.nby * s.nbx;
-    if (first != 2) {
+    if (first) {
         for (int b = threadIdx.x; b < nbins; b += blockDim.x) s.bin_fill[b] = 0;
         __syncthreads();
-    }
-    for (int k = threadIdx.x; k < s.n && first != 2; k += blockDim.x) {
-        int4 w = make_int4(0, 0, 0, 0);
-        int bin = -1;
-        bool dead = false;
-        double cy, cx;
-        if (first) {
-            cy = seeds_yx[2 * k]; cx = seeds_yx[2 * k + 1];
+        for (int k = threadIdx.x; k < s.n; k += blockDim.x) {
+            const double cy = seeds_yx[2 * k], cx = seeds_yx[2 * k + 1];
             s.cy[k] = cy; s.cx[k] = cx; s.c0[k] = 0.0; s.c1[k] = 0.0; s.c2[k] = 0.0;
-        } else {
-            int4 pw = s.win[k];
-            long long cnt = s.isum[3 * k];
-            if (pw.y <= pw.x && pw.w <= pw.z && cnt == 0) dead = true; // was already dead
-            else if (cnt == 0) dead = true;                              // lost every pixel: dead for good
-            else {
-                double dn = (double)cnt;
-                cy = __ddiv_rn((double)s.isum[3 * k + 1], dn);
-                cx = __ddiv_rn((double)s.isum[3 * k + 2], dn);
-                s.cy[k] = cy; s.cx[k] = cx;
-                s.c0[k] = __ddiv_rn(s.sums[3 * k], dn);
-                s.c1[k] = __ddiv_rn(s.sums[3 * k + 1], dn);
-                s.c2[k] = __ddiv_rn(s.sums[3 * k + 2], dn);
-            }
+            s.win[k] = make_window(cy, cx, s.step_y, s.step_x, s.H, s.W);
+            const int by = min(max((int)cy / s.B, 0), s.nby - 1), bx = min(max((int)cx / s.B, 0), s.nbx - 1);
+            s.bin_of[k] = by * s.nbx + bx;
+            atomicAdd(&s.bin_fill[by * s.nbx + bx], 1);
+            s.obb[k] = make_int4(INT_MAX, -1, INT_MAX, -1);
+            s.maxdc[k] = (unsigned long long)__double_as_longlong(1.0);
         }
-        if (!dead) {
-            w = make_window(cy, cx, s.step_y, s.step_x, s.H, s.W);
-            int by = min(max((int)cy / s.B, 0), s.nby - 1), bx = min(max((int)cx / s.B, 0), s.nbx - 1);
-            bin = by * s.nbx + bx;
-            atomicAdd(&s.bin_fill[bin], 1);
-        }
-        s.win[k] = w;
-        s.bin_of[k] = bin;
-        s.obb[k] = make_int4(INT_MAX, -1, INT_MAX, -1);
     }
     __syncthreads();
     // exclusive scan of bin counts: warp shuffles + one partial per warp, chunks of blockDim
@@ -146,12 +122,12 @@ __global__ void __launch_bounds__(1024) k_finalize_bin(KmState s, const double* 
         int bin = s.bin_of[k];
         if (bin < 0) continue;
         const int pos = s.bin_start[bin] + atomicAdd(&s.bin_fill[bin], 1);
-        s.bin_items[pos] = k;
         const int4 w = s.win[k];
         Cand c;
         c.cy = s.cy[k]; c.cx = s.cx[k]; c.c0 = s.c0[k]; c.c1 = s.c1[k]; c.c2 = s.c2[k];
         c.y0 = w.x; c.y1 = w.y; c.x0 = w.z; c.x1 = w.w; c.k = k; c.pad = 0;
         s.packed[pos] = c;
+        if (s.slico) s.packed_maxdc[pos] = __longlong_as_double((long long)s.maxdc[k]);
     }
     __syncthreads();
     for (int b = threadIdx.x; b < nbins; b += blockDim.x) s.bin_fill[b] = 0; // k_update counts the next sweep's bins from zero
@@ -164,9 +140,11 @@ __device__ __forceinline__ unsigned long long dbits(double v) { return (unsigned
 // assignment: one CTA (128 threads) per 32x32 tile; a thread owns one column and AROWS = 8 consecutive rows.
 // The tile's Lab values are staged in shared memory, candidates are visited nearest-first and the loop stops as soon as
 // the spatial lower bound of every remaining candidate exceeds the worst of the thread's current minima.
+template <bool SLICO>
 __global__ void __launch_bounds__(ATHREADS) k_assign(KmState s, const double* __restrict__ lab, int* __restrict__ labels)
 {
     __shared__ Cand cand[ACAP];
+    __shared__ double s_maxdc[SLICO ? ACAP : 1];
     __shared__ float s_key[ACAP];
     __shared__ double s_lb[ACAP];          // lower bound of the spatial term of the candidate at sorted position i, and of all later ones
     __shared__ unsigned char s_order[ACAP];
@@ -225,6 +203,7 @@ __global__ void __launch_bounds__(ATHREADS) k_assign(KmState s, const double* __
                     if ((c.y0 < ty1) && (c.y1 > ty0) && (c.x0 < tx1) && (c.x1 > tx0)) {
                         const int pos = atomicAdd(&s_ncand, 1);
                         cand[pos] = c;
+                        if (SLICO) s_maxdc[pos] = s.packed_maxdc[i];
                         const float fy = (float)c.cy - tcy, fx = (float)c.cx - tcx;
                         s_key[pos] = fy * fy + fx * fx;
                     }
@@ -251,6 +230,7 @@ __global__ void __launch_bounds__(ATHREADS) k_assign(KmState s, const double* __
                     if (ok) {
                         int pos = n + __popc(m & ((1u << lane) - 1u));
                         cand[pos] = c;
+                        if (SLICO) s_maxdc[pos] = s.packed_maxdc[i];
                         const float fy = (float)c.cy - tcy, fx = (float)c.cx - tcx;
                         s_key[pos] = fy * fy + fx * fx;
                     }
@@ -311,7 +291,7 @@ __global__ void __launch_bounds__(ATHREADS) k_assign(KmState s, const double* __
                     double dcol = __dmul_rn(d0, d0);
                     dcol = __dadd_rn(dcol, __dmul_rn(d1, d1));
                     dcol = __dadd_rn(dcol, __dmul_rn(d2, d2));
-                    const double dc = __dadd_rn(sp, dcol);
+                    const double dc = __dadd_rn(sp, SLICO ? __ddiv_rn(dcol, s_maxdc[c]) : dcol);
                     const unsigned long long bd = dbits(dc), bb = dbits(best[j]);
                     if (bd < bb || (bd == bb && bestk[j] >= 0 && ck < bestk[j])) { best[j] = dc; bestk[j] = ck; improved = true; }
                 }
@@ -415,8 +395,21 @@ __global__ void __launch_bounds__(256) k_update(KmState s, const double* __restr
         s.win[k] = w;
         s.bin_of[k] = bin;
         s.obb[k] = make_int4(INT_MAX, -1, INT_MAX, -1);
-        s.isum[3 * k] = cnt;
     }
+}
+
+// SLICO: after the centres moved, remember the largest colour distance inside every cluster (the original only ever raises it)
+__global__ void __launch_bounds__(256) k_slico_max(KmState s, const double* __restrict__ lab, const int* __restrict__ labels)
+{
+    const size_t HW = (size_t)s.H * s.W;
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int k = labels[p];
+    const double d0 = __dsub_rn(lab[p], s.c0[k]), d1 = __dsub_rn(lab[HW + p], s.c1[k]), d2 = __dsub_rn(lab[2 * HW + p], s.c2[k]);
+    double dcol = __dmul_rn(d0, d0);
+    dcol = __dadd_rn(dcol, __dmul_rn(d1, d1));
+    dcol = __dadd_rn(dcol, __dmul_rn(d2, d2));
+    if (dcol == dcol) atomicMax(&s.maxdc[k], (unsigned long long)__double_as_longlong(dcol));
 }
 
 __global__ void k_export_centroids(KmState s, double* out)
@@ -437,11 +430,12 @@ static size_t carve(KmState& s, void* ws, size_t bytes, int H, int W, int n, int
     s.cy = c.take<double>(n); s.cx = c.take<double>(n);
     s.c0 = c.take<double>(n); s.c1 = c.take<double>(n); s.c2 = c.take<double>(n);
     s.win = c.take<int4>(n); s.obb = c.take<int4>(n);
-    s.sums = c.take<double>(3 * (size_t)n); s.isum = c.take<long long>(3 * (size_t)n);
     s.bin_start = c.take<int>((size_t)s.nby * s.nbx + 1);
     s.bin_fill = c.take<int>((size_t)s.nby * s.nbx);
-    s.bin_items = c.take<int>(n); s.bin_of = c.take<int>(n);
+    s.bin_of = c.take<int>(n);
     s.packed = c.take<Cand>(n);
+    s.maxdc = c.take<unsigned long long>(n);
+    s.packed_maxdc = c.take<double>(n);
     return isb_align(c.off);
 }
 
@@ -459,22 +453,31 @@ extern "C" int isb_slic_kmeans(const double* lab_planar, int H, int W, const dou
 {
     ISB_REQUIRE(lab_planar && seeds_yx && labels && ws, "null pointer");
     ISB_REQUIRE(H > 0 && W > 0 && n_seeds > 0 && step_y > 0 && step_x > 0 && step > 0, "bad sizes");
-    if (slic_zero) { isb_set_error("slic_zero (SLICO) is not implemented on the device path"); return ISB_ERR_UNSUPPORTED; }
     KmState s;
     size_t need = carve(s, ws, ws_bytes, H, W, n_seeds, step_y, step_x);
     ISB_REQUIRE(need <= ws_bytes, "workspace too small");
     s.sw = 1.0 / (step * step);
+    s.slico = slic_zero ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     ISB_CUDA_CHECK(cudaMemsetAsync(labels, 0, sizeof(int32_t) * (size_t)H * W, st));
     k_finalize_bin<<<1, 1024, 0, st>>>(s, seeds_yx, 1);
     ISB_LAUNCH_CHECK();
     dim3 agrid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE);
     for (int it = 0; it < max_iter; ++it) {
-        { ProfScope p(ISB_PROF_ASSIGN, st); k_assign<<<agrid, ATHREADS, 0, st>>>(s, lab_planar, labels); }
+        {
+            ProfScope p(ISB_PROF_ASSIGN, st);
+            if (slic_zero) k_assign<true><<<agrid, ATHREADS, 0, st>>>(s, lab_planar, labels);
+            else k_assign<false><<<agrid, ATHREADS, 0, st>>>(s, lab_planar, labels);
+        }
         ISB_LAUNCH_CHECK();
         { ProfScope p(ISB_PROF_UPDATE, st); k_update<<<(n_seeds + 7) / 8, 256, 0, st>>>(s, lab_planar, labels); }
         ISB_LAUNCH_CHECK();
-        { ProfScope p(ISB_PROF_FINALIZE, st); k_finalize_bin<<<1, 1024, 0, st>>>(s, seeds_yx, 2); }
+        if (slic_zero) {
+            const size_t npx = (size_t)H * W;
+            k_slico_max<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(s, lab_planar, labels);
+            ISB_LAUNCH_CHECK();
+        }
+        { ProfScope p(ISB_PROF_FINALIZE, st); k_finalize_bin<<<1, 1024, 0, st>>>(s, seeds_yx, 0); }
         ISB_LAUNCH_CHECK();
     }
     if (centroids) {

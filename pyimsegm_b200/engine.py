@@ -65,7 +65,6 @@ class Engine(object):
         self.lib = _lib.lib()
         self.device = self.torch.device('cuda', self.torch.cuda.current_device() if device is None else device)
         self._bufs = {}
-        self._pinned = {}
 
     # -- memory helpers ------------------------------------------------------------------------------------------
     def buf(self, name, shape, dtype):

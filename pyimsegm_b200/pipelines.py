@@ -9,19 +9,19 @@ and return values):
 * :func:`segment_color2d_slic_features_model_graphcut`  (reference pipelines.py:160-241)
 * :func:`compute_color2d_superpixels_features`          (reference pipelines.py:244-270)
 
-The image goes to the device once; label map, features, graph, energies and the cut never leave it.  The only
-host round trip is the class model (scikit-learn, as in the reference): features [N, D] down, probabilities
-[N, K] up.
+The image goes to the device once; label map, features, class model, graph, energies and the cut never leave it and the
+host synchronises ONCE, when the results are downloaded.  (A user-supplied model, or one the device GMM does not cover, costs
+one round trip: features [N, D] down, probabilities [N, K] up.)
 """
 import logging
 
 import numpy as np
 
 from .descriptors import FEATURES_SET_COLOR, compute_selected_features_img2d, flags_are_native, native_feature_layout
-from .engine import EDGE_MODES, get_engine
+from .engine import get_engine
 from .graph_cuts import (_edge_mode, compute_pairwise_cost, device_gmm_applicable, estim_class_model,
                          segment_graph_cut_general)
-from .superpixels import _as_rgb_like, _supported_dtype, device_adjacency, slic_params
+from .superpixels import _as_rgb_like, _supported_dtype, slic_params
 
 #: basic features extracted from superpixels (reference pipelines.py:35)
 FTS_SET_SIMPLE = FEATURES_SET_COLOR

@@ -49,7 +49,7 @@ def segment_slic_img2d(img, sp_size=50, relative_compact=0.1, slico=False):
     :param ndarray img: input image [H, W, 3] or [H, W]
     :param int sp_size: superpixel initial size
     :param float relative_compact: relative regularisation in range (0, 1)
-    :param bool slico: parameter-free SLICO variant (not available on the device path)
+    :param bool slico: parameter-free SLICO / ASLIC variant (skimage's slic_zero)
     :return ndarray: segmentation [H, W], labels 0..N-1
     """
     img = _supported_dtype(_as_rgb_like(img))

@@ -13,14 +13,14 @@ def eng():
     return get_engine()
 
 
-def _slic_both(oracle, img, sp_size, regul):
+def _slic_both(oracle, img, sp_size, regul, slico=False):
     from pyimsegm_b200 import superpixels as sp
-    got = sp.segment_slic_img2d(img, sp_size, regul)
-    want = oracle.segment_slic_img2d(img, sp_size, regul)
+    got = sp.segment_slic_img2d(img, sp_size, regul, slico)
+    want = oracle.segment_slic_img2d(img, sp_size, regul, slico)
     return got, want
 
 
-@pytest.mark.parametrize('case', ['rand', 'disc', 'flat', 'u8', 'gray', 'odd'])
+@pytest.mark.parametrize('case', ['rand', 'disc', 'flat', 'u8', 'gray', 'odd', 'slico', 'slico_flat'])
 def test_slic_label_map_bit_exact(oracle, case):
     rng = np.random.RandomState(0)
     if case == 'rand':
@@ -35,6 +35,10 @@ def test_slic_label_map_bit_exact(oracle, case):
         img, args = (synth_disc(256, 256) * 255).astype(np.uint8), (30, 0.3)
     elif case == 'gray':
         img, args = synth_disc(128, 160)[..., 0], (20, 0.2)
+    elif case == 'slico':
+        img, args = synth_regions(180, 230, seed=6)[0], (15, 0.2, True)       # SLICO / ASLIC (slic_zero=True)
+    elif case == 'slico_flat':
+        img, args = synth_disc(150, 170, noise=0.0), (14, 0.3, True)
     else:
         img, args = synth_regions(203, 317, seed=5)[0], (17, 0.25)
     got, want = _slic_both(oracle, img, *args)
