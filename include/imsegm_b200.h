@@ -55,9 +55,14 @@ int isb_profile_collect(double* ms_out /* host */, long long* count_out /* host 
  *   lab_planar : out, [3,H,W] f64
  *   minmax_out : out, 4 doubles (device) -- [0] min and [1] max of the raw image ([2..3] scratch); max == min makes
  *                the result NaN
- *   rescale    : 1 = apply the reference wrapper's min-max rescale when (min != 0 or max != 1); 0 = never */
+ *   rescale    : 1 = apply the reference wrapper's min-max rescale when (min != 0 or max != 1); 0 = never;
+ *                2 = as 1 with the extrema the caller left in minmax_out[0..1] (row-band mode: the extrema of the whole
+ *                image, merged by a collective from isb_image_minmax of every band) */
 int isb_slic_prepare(const void* img, int dtype, int H, int W, int C, const double* w_half, int radius, double ratio,
                      int rescale, double* lab_planar, double* minmax_out /* room for 4 doubles */, isb_stream_t stream);
+
+/* minimum and maximum of n samples (NaN ignored) -> minmax_out[0..1]; [2..3] scratch */
+int isb_image_minmax(const void* img, int dtype, long long n, double* minmax_out /* room for 4 doubles */, isb_stream_t stream);
 
 size_t isb_slic_kmeans_workspace_bytes(int H, int W, int n_seeds, int step_y, int step_x);
 
@@ -68,6 +73,38 @@ size_t isb_slic_kmeans_workspace_bytes(int H, int W, int n_seeds, int step_y, in
 int isb_slic_kmeans(const double* lab_planar, int H, int W, const double* seeds_yx, int n_seeds, int step_y, int step_x,
                     double step, int max_iter, int slic_zero, int32_t* labels, double* centroids, void* ws, size_t ws_bytes,
                     isb_stream_t stream);
+
+/* Row-band form of the sweeps: one image taller than a GPU wants to hold (BASELINE config 5) is cut into
+ * row bands, one per GPU.  The cluster state (centres, windows, bins) is replicated in every band's workspace and lives in
+ * the coordinates of the whole image; a band holds pixel memory for its owned rows plus a halo of >= 2*step_y rows on either
+ * side, assigns every row of that slab and sums the clusters whose centre row it owns (all their members are inside the slab;
+ * a member further away -- an orphan that no window covers -- is counted in xchg[6 n_seeds] and the caller must then fall back
+ * to one GPU).  Per sweep:
+ *     isb_slic_band_assign -> isb_slic_band_update(xchg) -> [sum xchg as int64 over the bands] -> isb_slic_band_import(xchg)
+ *     -> (SLICO: [max of maxdc_xchg as int64/uint64 over the bands]) -> isb_slic_band_finalize
+ * xchg is [6*n_seeds + 1] int64: per cluster the bit patterns of (cy, cx, c0, c1, c2) and a state word (1 alive, 2 died),
+ * all zero in every band but the owner's, so the integer sum is an exact merge (and keeps -0.0 and NaN payloads).  The labels
+ * of the owned rows are bit-identical to isb_slic_kmeans on the whole image.  Workspace: isb_slic_kmeans_workspace_bytes of
+ * the WHOLE image (image_rows, width). */
+typedef struct isb_slic_band {
+    int32_t slab_rows, width;   /* pixel memory held by this band: rows [y_off, y_off + slab_rows) of the image */
+    int32_t image_rows, y_off;
+    int32_t own_lo, own_hi;     /* global rows whose clusters this band sums; the bands' [own_lo, own_hi) partition the image */
+    int32_t halo;               /* >= 2*step_y; the slab covers [own_lo - halo, own_hi + halo) clipped to the image */
+    int32_t n_seeds, step_y, step_x, slic_zero;
+    double step;
+    const double* lab_slab;     /* plane c, slab row y, column x at lab_slab[c*plane_stride + y*width + x] */
+    size_t plane_stride;
+    const double* seeds_yx;     /* [n_seeds,2] seeds of the whole image */
+    int32_t* labels_slab;       /* [slab_rows, width] */
+    void* ws; size_t ws_bytes;
+} isb_slic_band_t;
+int isb_slic_band_begin(const isb_slic_band_t* band, isb_stream_t stream);
+int isb_slic_band_assign(const isb_slic_band_t* band, isb_stream_t stream);
+int isb_slic_band_update(const isb_slic_band_t* band, int64_t* xchg, isb_stream_t stream);
+int isb_slic_band_import(const isb_slic_band_t* band, const int64_t* xchg, uint64_t* maxdc_xchg /* [n_seeds], SLICO only */,
+                         isb_stream_t stream);
+int isb_slic_band_finalize(const isb_slic_band_t* band, const uint64_t* maxdc_xchg, isb_stream_t stream);
 
 size_t isb_connectivity_workspace_bytes(int H, int W);
 
@@ -92,6 +129,17 @@ int isb_enforce_connectivity(const int32_t* labels, int H, int W, int min_size, 
 size_t isb_segment_stats_workspace_bytes(int nb);
 int isb_segment_stats_2d(const void* img, int dtype, const int32_t* seg, int H, int W, int nb, int flags, double* feat,
                          int ld, int col0, double* centres, int32_t* counts, void* ws, size_t ws_bytes, isb_stream_t stream);
+
+/* The same statistics with caller-owned accumulators, so that row bands of one image can be merged by a collective between
+ * the calls: acc [nb,6] f64 (sum c0..c2, sum of squares c0..c2), iacc [nb,3] i64 (count, sum row, sum col), var [nb,3] f64
+ * (squared deviations from the f32 mean).  accumulate / deviation ADD into acc+iacc / var (the caller zeroes them);
+ * rows are global rows [y_off, y_off + H) of the image for the row sums. */
+int isb_segment_stats_accumulate(const void* img, int dtype, const int32_t* seg, int H, int W, int y_off, int nb, double* acc,
+                                 int64_t* iacc, isb_stream_t stream);
+int isb_segment_stats_deviation(const void* img, int dtype, const int32_t* seg, int H, int W, int nb, const double* acc,
+                                const int64_t* iacc, float* meanf_scratch /* [nb,3] */, double* var, isb_stream_t stream);
+int isb_segment_stats_finish(int nb, int flags, const double* acc, const double* var, const int64_t* iacc, double* feat, int ld,
+                             int col0, double* centres, int32_t* counts, isb_stream_t stream);
 
 /* computeGrayImage3dMean :144 / Energy :169 / Variance :194 of features_cython.pyx: one channel, any rank (n voxels).
  *   flags bit0 mean, bit1 std, bit2 energy -> columns col0.. of feat [nb, ld] in that order */
@@ -185,6 +233,10 @@ int isb_lm_texture(const void* img, int dtype, const int32_t* seg, int H, int W,
 
 /* dst[0..n) = value (initial labeling of isb_alpha_expansion and similar small fills) */
 int isb_fill_i32(int32_t* dst, long long n, int32_t value, isb_stream_t stream);
+
+/* dst[i] = dst[i] (op) src[i] over n 8-byte words; op 0 int64 sum, 1 int64 max, 2 f64 min, 3 f64 max, 4 f64 sum.  What a
+ * collective does between GPUs in row-band mode, for several bands held by one GPU. */
+int isb_combine(void* dst, const void* src, long long n, int op, isb_stream_t stream);
 
 /* final LUT gathers of imsegm/pipelines.py:104,109:  segm = graph_labels[slic], segm_soft = proba[slic]
  *   lut_i [nb] i32 (optional), lut_p [nb,K] f64 (optional); outputs [H,W] i32 / [H,W,K] f64 */

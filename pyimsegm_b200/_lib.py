@@ -17,6 +17,19 @@ DTYPE_CODES = {'uint8': 0, 'uint16': 1, 'float32': 2, 'float64': 3}
 
 _vp, _i, _d, _sz, _ll = C.c_void_p, C.c_int, C.c_double, C.c_size_t, C.c_longlong
 
+
+
+class SlicBand(C.Structure):
+    """isb_slic_band_t of include/imsegm_b200.h"""
+    _fields_ = [('slab_rows', C.c_int32), ('width', C.c_int32), ('image_rows', C.c_int32), ('y_off', C.c_int32),
+                ('own_lo', C.c_int32), ('own_hi', C.c_int32), ('halo', C.c_int32),
+                ('n_seeds', C.c_int32), ('step_y', C.c_int32), ('step_x', C.c_int32), ('slic_zero', C.c_int32),
+                ('step', C.c_double), ('lab_slab', C.c_void_p), ('plane_stride', C.c_size_t), ('seeds_yx', C.c_void_p),
+                ('labels_slab', C.c_void_p), ('ws', C.c_void_p), ('ws_bytes', C.c_size_t)]
+
+
+_bp = C.POINTER(SlicBand)
+
 #: every symbol declared in include/imsegm_b200.h: name -> (restype, argtypes)
 SIGNATURES = {
     'isb_last_error': (C.c_char_p, []),
@@ -27,6 +40,15 @@ SIGNATURES = {
     'isb_profile_stage_name': (C.c_char_p, [_i]),
     'isb_profile_collect': (_i, [C.POINTER(_d), C.POINTER(_ll)]),
     'isb_slic_prepare': (_i, [_vp, _i, _i, _i, _i, C.POINTER(_d), _i, _d, _i, _vp, _vp, _vp]),
+    'isb_image_minmax': (_i, [_vp, _i, _ll, _vp, _vp]),
+    'isb_slic_band_begin': (_i, [_bp, _vp]),
+    'isb_slic_band_assign': (_i, [_bp, _vp]),
+    'isb_slic_band_update': (_i, [_bp, _vp, _vp]),
+    'isb_slic_band_import': (_i, [_bp, _vp, _vp, _vp]),
+    'isb_slic_band_finalize': (_i, [_bp, _vp, _vp]),
+    'isb_segment_stats_accumulate': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'isb_segment_stats_deviation': (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    'isb_segment_stats_finish': (_i, [_i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     'isb_slic_kmeans_workspace_bytes': (_sz, [_i, _i, _i, _i, _i]),
     'isb_slic_kmeans': (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     'isb_connectivity_workspace_bytes': (_sz, [_i, _i]),
@@ -45,6 +67,7 @@ SIGNATURES = {
     'isb_lm_workspace_bytes': (_sz, [_i, _i, _i, _i]),
     'isb_lm_texture': (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, C.POINTER(_d), _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _sz, _vp]),
     'isb_fill_i32': (_i, [_vp, _ll, _i, _vp]),
+    'isb_combine': (_i, [_vp, _vp, _ll, _i, _vp]),
     'isb_gray_stats_workspace_bytes': (_sz, [_i]),
     'isb_gray_stats': (_i, [_vp, _i, _vp, _ll, _i, _i, _vp, _i, _i, _vp, _sz, _vp]),
     'isb_label_hist_2d': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),

@@ -322,6 +322,26 @@ extern "C" int isb_fill_i32(int32_t* dst, long long n, int32_t value, isb_stream
     return ISB_OK;
 }
 
+// dst = dst (op) src on 8-byte words: the in-process stand-in for the collectives of the row-band mode (several bands on one GPU)
+__global__ void k_combine(void* dst, const void* src, long long n, int op)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (op == 0) ((long long*)dst)[i] += ((const long long*)src)[i];
+    else if (op == 1) { long long a = ((long long*)dst)[i], b = ((const long long*)src)[i]; ((long long*)dst)[i] = a > b ? a : b; }
+    else if (op == 2) ((double*)dst)[i] = fmin(((double*)dst)[i], ((const double*)src)[i]);
+    else if (op == 3) ((double*)dst)[i] = fmax(((double*)dst)[i], ((const double*)src)[i]);
+    else ((double*)dst)[i] = ((double*)dst)[i] + ((const double*)src)[i];
+}
+
+extern "C" int isb_combine(void* dst, const void* src, long long n, int op, isb_stream_t stream)
+{
+    ISB_REQUIRE(dst && src && n > 0 && op >= 0 && op <= 4, "bad arguments");
+    k_combine<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dst, src, n, op);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
 extern "C" int isb_gather(const int32_t* seg, long long npx, const int32_t* lut_i, const double* lut_p, int K, int32_t* out_i,
                           double* out_p, isb_stream_t stream)
 {

@@ -27,7 +27,7 @@ struct StatWs {
 __device__ __forceinline__ float clean(float v) { return isnan(v) ? 0.0f : v; } // np.nan_to_num (descriptors.py:824)
 
 __global__ void __launch_bounds__(256) k_stats_pass1(const void* __restrict__ img, int dtype, const int* __restrict__ seg, int H, int W,
-                                                     StatWs ws)
+                                                     int y_off, StatWs ws)
 {
     const int x = blockIdx.x * 256 + threadIdx.x;
     if (x >= W) return;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) k_stats_pass1(const void* __restrict__ im
         if (y < y1) {
             s0 += (double)v0; s1 += (double)v1; s2 += (double)v2;
             e0 += (double)__fmul_rn(v0, v0); e1 += (double)__fmul_rn(v1, v1); e2 += (double)__fmul_rn(v2, v2);
-            cnt += 1; sy += y;
+            cnt += 1; sy += y + y_off;
         }
     }
 }
@@ -171,7 +171,7 @@ extern "C" int isb_segment_stats_2d(const void* img, int dtype, const int32_t* s
     ProfScope prof(ISB_PROF_STATS, st);
     ISB_CUDA_CHECK(cudaMemsetAsync(ws, 0, need, st));
     dim3 grid((W + 255) / 256, (H + SROWS - 1) / SROWS);
-    k_stats_pass1<<<grid, 256, 0, st>>>(img, dtype, seg, H, W, w);
+    k_stats_pass1<<<grid, 256, 0, st>>>(img, dtype, seg, H, W, 0, w);
     ISB_LAUNCH_CHECK();
     if (flags & 2) {
         k_stats_means<<<(nb + 255) / 256, 256, 0, st>>>(nb, w);
@@ -179,6 +179,55 @@ extern "C" int isb_segment_stats_2d(const void* img, int dtype, const int32_t* s
         k_stats_pass2<<<grid, 256, 0, st>>>(img, dtype, seg, H, W, w);
         ISB_LAUNCH_CHECK();
     }
+    k_stats_finalize<<<(nb + 255) / 256, 256, 0, st>>>(nb, flags, w, feat, ld, col0, centres, counts);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
+// ---- caller-owned accumulators (row bands of one image merged by a collective between the calls) -------------------------
+
+extern "C" int isb_segment_stats_accumulate(const void* img, int dtype, const int32_t* seg, int H, int W, int y_off, int nb, double* acc,
+                                            int64_t* iacc, isb_stream_t stream)
+{
+    ISB_REQUIRE(seg && acc && iacc, "null pointer");
+    ISB_REQUIRE(H > 0 && W > 0 && nb > 0 && y_off >= 0, "bad sizes");
+    ISB_REQUIRE(dtype >= ISB_U8 && dtype <= ISB_F64, "bad dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ISB_PROF_STATS, st);
+    StatWs w;
+    w.acc = acc; w.iacc = (long long*)iacc; w.var = nullptr; w.meanf = nullptr;
+    dim3 grid((W + 255) / 256, (H + SROWS - 1) / SROWS);
+    k_stats_pass1<<<grid, 256, 0, st>>>(img, dtype, seg, H, W, y_off, w);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
+extern "C" int isb_segment_stats_deviation(const void* img, int dtype, const int32_t* seg, int H, int W, int nb, const double* acc,
+                                           const int64_t* iacc, float* meanf_scratch, double* var, isb_stream_t stream)
+{
+    ISB_REQUIRE(img && seg && acc && iacc && meanf_scratch && var, "null pointer");
+    ISB_REQUIRE(H > 0 && W > 0 && nb > 0, "bad sizes");
+    ISB_REQUIRE(dtype >= ISB_U8 && dtype <= ISB_F64, "bad dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ISB_PROF_STATS, st);
+    StatWs w;
+    w.acc = (double*)acc; w.iacc = (long long*)iacc; w.var = var; w.meanf = meanf_scratch;
+    k_stats_means<<<(nb + 255) / 256, 256, 0, st>>>(nb, w);
+    ISB_LAUNCH_CHECK();
+    dim3 grid((W + 255) / 256, (H + SROWS - 1) / SROWS);
+    k_stats_pass2<<<grid, 256, 0, st>>>(img, dtype, seg, H, W, w);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
+extern "C" int isb_segment_stats_finish(int nb, int flags, const double* acc, const double* var, const int64_t* iacc, double* feat, int ld,
+                                        int col0, double* centres, int32_t* counts, isb_stream_t stream)
+{
+    ISB_REQUIRE(acc && iacc && (var || !(flags & 2)), "null pointer");
+    ISB_REQUIRE(nb > 0, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    StatWs w;
+    w.acc = (double*)acc; w.iacc = (long long*)iacc; w.var = (double*)var; w.meanf = nullptr;
     k_stats_finalize<<<(nb + 255) / 256, 256, 0, st>>>(nb, flags, w, feat, ld, col0, centres, counts);
     ISB_LAUNCH_CHECK();
     return ISB_OK;

@@ -50,6 +50,11 @@ struct KmState {
     int slico;
     int n, H, W, step_y, step_x, B, nby, nbx;
     double sw;       // spatial weight 1/step^2
+    // Row-band mode (one band of a taller image per GPU, isb_slic_band_*): pixel memory is a slab of H rows whose row 0 is
+    // global row y_off of an image Hg rows tall; cluster geometry (centres, windows, bins) is always global.  The
+    // monolithic path is the band [0, H) of itself: y_off = 0, Hg = H, pstride = H * W.
+    int Hg, y_off, own_lo, own_hi, halo;
+    size_t pstride;  // distance between the Lab planes, in doubles
 };
 
 __device__ __forceinline__ int4 make_window(double cy, double cx, int step_y, int step_x, int H, int W)
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(1024) k_finalize_bin(KmState s, const double* 
         for (int k = threadIdx.x; k < s.n; k += blockDim.x) {
             const double cy = seeds_yx[2 * k], cx = seeds_yx[2 * k + 1];
             s.cy[k] = cy; s.cx[k] = cx; s.c0[k] = 0.0; s.c1[k] = 0.0; s.c2[k] = 0.0;
-            s.win[k] = make_window(cy, cx, s.step_y, s.step_x, s.H, s.W);
+            s.win[k] = make_window(cy, cx, s.step_y, s.step_x, s.Hg, s.W);
             const int by = min(max((int)cy / s.B, 0), s.nby - 1), bx = min(max((int)cx / s.B, 0), s.nbx - 1);
             s.bin_of[k] = by * s.nbx + bx;
             atomicAdd(&s.bin_fill[by * s.nbx + bx], 1);
@@ -151,9 +156,10 @@ __global__ void __launch_bounds__(ATHREADS) k_assign(KmState s, const double* __
     __shared__ double s_px[3][TILE][TILE]; // Lab of the tile
     __shared__ int s_ncand, s_done, s_row, s_off, s_total;
     const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
-    const int tx1 = min(tx0 + TILE, s.W), ty1 = min(ty0 + TILE, s.H);
+    const int tx1 = min(tx0 + TILE, s.W);
+    const int gy0 = ty0 + s.y_off, gy1 = min(ty0 + TILE, s.H) + s.y_off; // the tile's rows in global coordinates
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t HW = (size_t)s.H * s.W;
+    const size_t HW = s.pstride;
     const int x = tx0 + lane;
     const bool xin = x < s.W;
     const int yb = ty0 + warp * AROWS; // first row of this thread
@@ -177,9 +183,9 @@ __global__ void __launch_bounds__(ATHREADS) k_assign(KmState s, const double* __
         }
     }
     // bins that can hold a centroid whose window reaches this tile (superset; the exact window test follows)
-    const int by0 = max(ty0 - 2 * s.step_y - 2, 0) / s.B, by1 = min(ty1 + 2 * s.step_y + 1, s.H - 1) / s.B;
+    const int by0 = max(gy0 - 2 * s.step_y - 2, 0) / s.B, by1 = min(gy1 + 2 * s.step_y + 1, s.Hg - 1) / s.B;
     const int bx0 = max(tx0 - 2 * s.step_x - 2, 0) / s.B, bx1 = min(tx1 + 2 * s.step_x + 1, s.W - 1) / s.B;
-    const float tcy = 0.5f * (ty0 + ty1 - 1), tcx = 0.5f * (tx0 + tx1 - 1);
+    const float tcy = 0.5f * (gy0 + gy1 - 1), tcx = 0.5f * (tx0 + tx1 - 1);
     const int byl = min(by1, s.nby - 1), bxl = min(bx1, s.nbx - 1);
     // how many clusters sit in the bin rows that can reach this tile (bins of one row are contiguous in bin order)
     if (threadIdx.x == 0) { s_row = by0; s_off = 0; s_done = 0; s_ncand = 0; s_total = 0; }
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(ATHREADS) k_assign(KmState s, const double* __
                 const int beg = s.bin_start[row * s.nbx + bx0], end = s.bin_start[row * s.nbx + bxl + 1];
                 for (int i = beg + lane; i < end; i += 32) {
                     const Cand c = s.packed[i];
-                    if ((c.y0 < ty1) && (c.y1 > ty0) && (c.x0 < tx1) && (c.x1 > tx0)) {
+                    if ((c.y0 < gy1) && (c.y1 > gy0) && (c.x0 < tx1) && (c.x1 > tx0)) {
                         const int pos = atomicAdd(&s_ncand, 1);
                         cand[pos] = c;
                         if (SLICO) s_maxdc[pos] = s.packed_maxdc[i];
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(ATHREADS) k_assign(KmState s, const double* __
                     Cand c;
                     if (i < end && lane < room) {
                         c = s.packed[i];
-                        ok = (c.y0 < ty1) && (c.y1 > ty0) && (c.x0 < tx1) && (c.x1 > tx0);
+                        ok = (c.y0 < gy1) && (c.y1 > gy0) && (c.x0 < tx1) && (c.x1 > tx0);
                     }
                     unsigned m = __ballot_sync(0xffffffffu, ok);
                     if (ok) {
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(ATHREADS) k_assign(KmState s, const double* __
                 bool improved = false;
 #pragma unroll
                 for (int j = 0; j < AROWS; ++j) {
-                    const int y = yb + j;
+                    const int y = yb + j + s.y_off;
                     if (y < cy0 || y >= cy1) continue;
                     const double ty = __dsub_rn(ccy, (double)y);
                     const double sp = __dmul_rn(__dadd_rn(__dmul_rn(ty, ty), dx2), s.sw);
@@ -328,8 +334,14 @@ __global__ void __launch_bounds__(ATHREADS) k_assign(KmState s, const double* __
     }
 }
 
-// centroid sums: one warp per cluster, raster-order sequential double adds (see header)
-__global__ void __launch_bounds__(256) k_update(KmState s, const double* __restrict__ lab, const int* __restrict__ labels)
+// centroid sums: one warp per cluster, raster-order sequential double adds (see header).
+// BAND: this GPU holds a row band of the image.  A cluster is summed by the band that owns the row of its centre (every
+// member lies within 2*step rows of the centre the assignment used, i.e. inside that band's slab -- checked, violations are
+// counted in xchg[6n]); the result goes to the exchange record xchg[6k..6k+5] = bits(cy, cx, c0, c1, c2), state (1 alive,
+// 2 died) and every other band leaves zeros there, so that an integer sum over the bands is an exact merge.
+template <bool BAND>
+__global__ void __launch_bounds__(256) k_update(KmState s, const double* __restrict__ lab, const int* __restrict__ labels,
+                                                long long* __restrict__ xchg)
 {
     __shared__ double buf[8][3][32];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
@@ -337,8 +349,19 @@ __global__ void __launch_bounds__(256) k_update(KmState s, const double* __restr
     if (k >= s.n) return;
     // the box of this cluster's members, gathered by k_assign (empty when the cluster has no pixel)
     const int4 o = s.obb[k];
+    if (BAND) {
+        __syncwarp(); // every lane has its copy of the box before lane 0 resets it
+        const bool alive = s.bin_of[k] >= 0;
+        const int cr = alive ? (int)s.cy[k] : 0;   // row of the centre the assignment used
+        if (lane == 0) {
+            if (o.y >= o.x && (!alive || o.x + s.y_off < cr - s.halo || o.y + s.y_off > cr + s.halo))
+                atomicAdd((unsigned long long*)&xchg[6 * (size_t)s.n], 1ull);
+            s.obb[k] = make_int4(INT_MAX, -1, INT_MAX, -1);
+        }
+        if (!alive || cr < s.own_lo || cr >= s.own_hi) return;
+    }
     const int y0 = o.x, y1 = o.y + 1, x0 = o.z, x1 = o.w + 1;
-    const size_t HW = (size_t)s.H * s.W;
+    const size_t HW = s.pstride;
     double acc = 0.0;
     long long cnt = 0, sy = 0, sx = 0;
     // the box is walked in raster order, 32 pixels at a time; the label load of the next chunk is issued before the current
@@ -368,7 +391,7 @@ __global__ void __launch_bounds__(256) k_update(KmState s, const double* __restr
             sx += x;
         }
         cnt += nm;
-        sy += (long long)cy_ * nm;
+        sy += (long long)(cy_ + s.y_off) * nm;
         __syncwarp();
         if (lane < 3)
             for (int i = 0; i < nm; ++i) acc = __dadd_rn(acc, buf[wl][lane][i]);
@@ -379,6 +402,19 @@ __global__ void __launch_bounds__(256) k_update(KmState s, const double* __restr
     // centroid = sums / count with IEEE divisions (the original divides every feature by the element count), new window,
     // bin of the new centre; a cluster without pixels is dead for good
     const double a0 = __shfl_sync(0xffffffffu, acc, 0), a1 = __shfl_sync(0xffffffffu, acc, 1), a2 = __shfl_sync(0xffffffffu, acc, 2);
+    if (BAND) {
+        if (lane == 0) {
+            long long* r = xchg + 6 * (size_t)k;
+            if (cnt > 0) {
+                const double dn = (double)cnt;
+                r[0] = __double_as_longlong(__ddiv_rn((double)sy, dn)); r[1] = __double_as_longlong(__ddiv_rn((double)sx, dn));
+                r[2] = __double_as_longlong(__ddiv_rn(a0, dn)); r[3] = __double_as_longlong(__ddiv_rn(a1, dn));
+                r[4] = __double_as_longlong(__ddiv_rn(a2, dn));
+                r[5] = 1;
+            } else r[5] = 2;
+        }
+        return;
+    }
     if (lane == 0) {
         int4 w = make_int4(0, 0, 0, 0);
         int bin = -1;
@@ -387,7 +423,7 @@ __global__ void __launch_bounds__(256) k_update(KmState s, const double* __restr
             const double cy = __ddiv_rn((double)sy, dn), cx = __ddiv_rn((double)sx, dn);
             s.cy[k] = cy; s.cx[k] = cx;
             s.c0[k] = __ddiv_rn(a0, dn); s.c1[k] = __ddiv_rn(a1, dn); s.c2[k] = __ddiv_rn(a2, dn);
-            w = make_window(cy, cx, s.step_y, s.step_x, s.H, s.W);
+            w = make_window(cy, cx, s.step_y, s.step_x, s.Hg, s.W);
             const int by = min(max((int)cy / s.B, 0), s.nby - 1), bx = min(max((int)cx / s.B, 0), s.nbx - 1);
             bin = by * s.nbx + bx;
             atomicAdd(&s.bin_fill[bin], 1);
@@ -398,12 +434,38 @@ __global__ void __launch_bounds__(256) k_update(KmState s, const double* __restr
     }
 }
 
+// band mode: take the merged exchange records (see k_update<true>) into the replicated cluster state
+__global__ void k_import(KmState s, const long long* __restrict__ xchg)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= s.n) return;
+    const long long* r = xchg + 6 * (size_t)k;
+    const long long state = r[5];
+    if (state == 1) {
+        const double cy = __longlong_as_double(r[0]), cx = __longlong_as_double(r[1]);
+        s.cy[k] = cy; s.cx[k] = cx;
+        s.c0[k] = __longlong_as_double(r[2]); s.c1[k] = __longlong_as_double(r[3]); s.c2[k] = __longlong_as_double(r[4]);
+        s.win[k] = make_window(cy, cx, s.step_y, s.step_x, s.Hg, s.W);
+        const int by = min(max((int)cy / s.B, 0), s.nby - 1), bx = min(max((int)cx / s.B, 0), s.nbx - 1);
+        s.bin_of[k] = by * s.nbx + bx;
+        atomicAdd(&s.bin_fill[by * s.nbx + bx], 1);
+    } else {
+        // 2: the owner found no member, the cluster is dead for good; 0: it was dead already.  (An alive cluster always has
+        // exactly one owner, so 0 cannot occur for it.)
+        s.win[k] = make_int4(0, 0, 0, 0);
+        s.bin_of[k] = -1;
+    }
+}
+
 // SLICO: after the centres moved, remember the largest colour distance inside every cluster (the original only ever raises it)
 __global__ void __launch_bounds__(256) k_slico_max(KmState s, const double* __restrict__ lab, const int* __restrict__ labels)
 {
-    const size_t HW = (size_t)s.H * s.W;
-    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= HW) return;
+    // the rows this band owns (all of them on the monolithic path)
+    const size_t HW = s.pstride;
+    const size_t first = (size_t)(s.own_lo - s.y_off) * s.W, npx = (size_t)(s.own_hi - s.own_lo) * s.W;
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npx) return;
+    const size_t p = first + q;
     const int k = labels[p];
     const double d0 = __dsub_rn(lab[p], s.c0[k]), d1 = __dsub_rn(lab[HW + p], s.c1[k]), d2 = __dsub_rn(lab[2 * HW + p], s.c2[k]);
     double dcol = __dmul_rn(d0, d0);
@@ -423,7 +485,9 @@ __global__ void k_export_centroids(KmState s, double* out)
 static size_t carve(KmState& s, void* ws, size_t bytes, int H, int W, int n, int step_y, int step_x)
 {
     WsCarver c(ws, bytes);
+    // H here is the height the cluster geometry lives in (the whole image); band callers overwrite the slab fields afterwards
     s.n = n; s.H = H; s.W = W; s.step_y = step_y; s.step_x = step_x;
+    s.Hg = H; s.y_off = 0; s.own_lo = 0; s.own_hi = H; s.halo = 0; s.pstride = (size_t)H * W;
     s.B = 2 * (step_y > step_x ? step_y : step_x); // bin edge: coarse enough that the per-sweep scan over the bins is short
     if (s.B < 16) s.B = 16;
     s.nby = (H + s.B - 1) / s.B; s.nbx = (W + s.B - 1) / s.B;
@@ -470,7 +534,7 @@ extern "C" int isb_slic_kmeans(const double* lab_planar, int H, int W, const dou
             else k_assign<false><<<agrid, ATHREADS, 0, st>>>(s, lab_planar, labels);
         }
         ISB_LAUNCH_CHECK();
-        { ProfScope p(ISB_PROF_UPDATE, st); k_update<<<(n_seeds + 7) / 8, 256, 0, st>>>(s, lab_planar, labels); }
+        { ProfScope p(ISB_PROF_UPDATE, st); k_update<false><<<(n_seeds + 7) / 8, 256, 0, st>>>(s, lab_planar, labels, nullptr); }
         ISB_LAUNCH_CHECK();
         if (slic_zero) {
             const size_t npx = (size_t)H * W;
@@ -484,5 +548,103 @@ extern "C" int isb_slic_kmeans(const double* lab_planar, int H, int W, const dou
         k_export_centroids<<<(n_seeds + 255) / 256, 256, 0, st>>>(s, centroids);
         ISB_LAUNCH_CHECK();
     }
+    return ISB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Row-band mode: the same sweeps with one band of the image per GPU.  The cluster state is replicated; what crosses the
+// GPUs each sweep is the exchange buffer of k_update<true> (summed as int64 by the caller's collective).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+static int band_state(const isb_slic_band_t* b, KmState& s)
+{
+    ISB_REQUIRE(b && b->lab_slab && b->seeds_yx && b->labels_slab && b->ws, "null pointer");
+    ISB_REQUIRE(b->slab_rows > 0 && b->width > 0 && b->image_rows > 0 && b->n_seeds > 0 && b->step_y > 0 && b->step_x > 0 && b->step > 0,
+                "bad sizes");
+    ISB_REQUIRE(b->y_off >= 0 && b->y_off + b->slab_rows <= b->image_rows, "slab outside the image");
+    ISB_REQUIRE(b->own_lo >= b->y_off && b->own_hi <= b->y_off + b->slab_rows && b->own_lo < b->own_hi, "owned rows outside the slab");
+    ISB_REQUIRE(b->halo >= 2 * b->step_y, "halo must be at least 2 * step_y rows");
+    ISB_REQUIRE(b->y_off <= (b->own_lo - b->halo > 0 ? b->own_lo - b->halo : 0), "slab does not cover the halo above the owned rows");
+    ISB_REQUIRE(b->y_off + b->slab_rows >= (b->own_hi + b->halo < b->image_rows ? b->own_hi + b->halo : b->image_rows),
+                "slab does not cover the halo below the owned rows");
+    ISB_REQUIRE(b->plane_stride >= (size_t)b->slab_rows * b->width, "plane stride smaller than the slab");
+    size_t need = carve(s, b->ws, b->ws_bytes, b->image_rows, b->width, b->n_seeds, b->step_y, b->step_x);
+    ISB_REQUIRE(need <= b->ws_bytes, "workspace too small");
+    s.H = b->slab_rows; s.Hg = b->image_rows; s.y_off = b->y_off; s.own_lo = b->own_lo; s.own_hi = b->own_hi; s.halo = b->halo;
+    s.pstride = b->plane_stride;
+    s.sw = 1.0 / (b->step * b->step);
+    s.slico = b->slic_zero ? 1 : 0;
+    return ISB_OK;
+}
+
+} // namespace
+
+extern "C" int isb_slic_band_begin(const isb_slic_band_t* b, isb_stream_t stream)
+{
+    KmState s;
+    if (int rc = band_state(b, s)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    ISB_CUDA_CHECK(cudaMemsetAsync(b->labels_slab, 0, sizeof(int32_t) * (size_t)b->slab_rows * b->width, st));
+    k_finalize_bin<<<1, 1024, 0, st>>>(s, b->seeds_yx, 1);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
+extern "C" int isb_slic_band_assign(const isb_slic_band_t* b, isb_stream_t stream)
+{
+    KmState s;
+    if (int rc = band_state(b, s)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 agrid((s.W + TILE - 1) / TILE, (s.H + TILE - 1) / TILE);
+    ProfScope p(ISB_PROF_ASSIGN, st);
+    if (s.slico) k_assign<true><<<agrid, ATHREADS, 0, st>>>(s, b->lab_slab, b->labels_slab);
+    else k_assign<false><<<agrid, ATHREADS, 0, st>>>(s, b->lab_slab, b->labels_slab);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
+extern "C" int isb_slic_band_update(const isb_slic_band_t* b, int64_t* xchg, isb_stream_t stream)
+{
+    KmState s;
+    if (int rc = band_state(b, s)) return rc;
+    ISB_REQUIRE(xchg, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope p(ISB_PROF_UPDATE, st);
+    ISB_CUDA_CHECK(cudaMemsetAsync(xchg, 0, sizeof(int64_t) * (6 * (size_t)s.n + 1), st));
+    k_update<true><<<(s.n + 7) / 8, 256, 0, st>>>(s, b->lab_slab, b->labels_slab, (long long*)xchg);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
+extern "C" int isb_slic_band_import(const isb_slic_band_t* b, const int64_t* xchg, uint64_t* maxdc_xchg, isb_stream_t stream)
+{
+    KmState s;
+    if (int rc = band_state(b, s)) return rc;
+    ISB_REQUIRE(xchg && (!s.slico || maxdc_xchg), "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_import<<<(s.n + 255) / 256, 256, 0, st>>>(s, (const long long*)xchg);
+    ISB_LAUNCH_CHECK();
+    if (s.slico) {
+        const size_t npx = (size_t)(s.own_hi - s.own_lo) * s.W;
+        k_slico_max<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(s, b->lab_slab, b->labels_slab);
+        ISB_LAUNCH_CHECK();
+        ISB_CUDA_CHECK(cudaMemcpyAsync(maxdc_xchg, s.maxdc, sizeof(uint64_t) * (size_t)s.n, cudaMemcpyDeviceToDevice, st));
+    }
+    return ISB_OK;
+}
+
+extern "C" int isb_slic_band_finalize(const isb_slic_band_t* b, const uint64_t* maxdc_xchg, isb_stream_t stream)
+{
+    KmState s;
+    if (int rc = band_state(b, s)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s.slico) {
+        ISB_REQUIRE(maxdc_xchg, "null pointer");
+        ISB_CUDA_CHECK(cudaMemcpyAsync(s.maxdc, maxdc_xchg, sizeof(uint64_t) * (size_t)s.n, cudaMemcpyDeviceToDevice, st));
+    }
+    ProfScope p(ISB_PROF_FINALIZE, st);
+    k_finalize_bin<<<1, 1024, 0, st>>>(s, b->seeds_yx, 0);
+    ISB_LAUNCH_CHECK();
     return ISB_OK;
 }

@@ -210,7 +210,30 @@ __global__ void __launch_bounds__(256) k_blur_lab(const void* img, int dtype, in
     }
 }
 
+static int minmax_launch(const void* img, int dtype, size_t n, double* minmax_out, cudaStream_t st)
+{
+    // the two ordered-uint64 accumulators live in minmax_out[2..3]
+    unsigned long long* mm = (unsigned long long*)(minmax_out + 2);
+    ISB_CUDA_CHECK(cudaMemsetAsync(mm, 0xFF, sizeof(unsigned long long), st));
+    ISB_CUDA_CHECK(cudaMemsetAsync(mm + 1, 0x00, sizeof(unsigned long long), st));
+    int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    k_minmax<<<blocks, 256, 0, st>>>(img, dtype, n, mm);
+    ISB_LAUNCH_CHECK();
+    k_minmax_decode<<<1, 1, 0, st>>>(mm, minmax_out);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
 } // namespace
+
+extern "C" int isb_image_minmax(const void* img, int dtype, long long n, double* minmax_out, isb_stream_t stream)
+{
+    ISB_REQUIRE(img && minmax_out && n > 0, "null pointer or empty image");
+    ISB_REQUIRE(dtype >= ISB_U8 && dtype <= ISB_F64, "bad dtype");
+    return minmax_launch(img, dtype, (size_t)n, minmax_out, (cudaStream_t)stream);
+}
 
 extern "C" int isb_slic_prepare(const void* img, int dtype, int H, int W, int C, const double* w_half, int radius, double ratio,
                                 int rescale, double* lab_planar, double* minmax_out, isb_stream_t stream)
@@ -220,19 +243,10 @@ extern "C" int isb_slic_prepare(const void* img, int dtype, int H, int W, int C,
     ISB_REQUIRE(dtype >= ISB_U8 && dtype <= ISB_F64, "bad dtype");
     ISB_REQUIRE(radius >= 0 && radius <= 8 && (radius == 0 || w_half), "gaussian radius must be in [0,8]");
     cudaStream_t st = (cudaStream_t)stream;
-    // the two ordered-uint64 accumulators live in the tail of minmax_out's own allocation? no: keep them separate,
     // minmax_out must have room for 4 doubles: [min, max, scratch, scratch]
     ProfScope prof(ISB_PROF_PREPARE, st);
-    unsigned long long* mm = (unsigned long long*)(minmax_out + 2);
-    ISB_CUDA_CHECK(cudaMemsetAsync(mm, 0xFF, sizeof(unsigned long long), st));
-    ISB_CUDA_CHECK(cudaMemsetAsync(mm + 1, 0x00, sizeof(unsigned long long), st));
-    size_t n = (size_t)H * W * C;
-    int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    k_minmax<<<blocks, 256, 0, st>>>(img, dtype, n, mm);
-    ISB_LAUNCH_CHECK();
-    k_minmax_decode<<<1, 1, 0, st>>>(mm, minmax_out);
-    ISB_LAUNCH_CHECK();
+    if (rescale != 2)
+        if (int rc = minmax_launch(img, dtype, (size_t)H * W * C, minmax_out, st)) return rc;
     GaussW gw;
     gw.r = radius;
     for (int i = 0; i < 9; ++i) gw.w[i] = (i <= radius && w_half) ? w_half[i] : 0.0;
