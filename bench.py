@@ -296,6 +296,88 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_tiled(args):
+    """extra workload (not the headline line): BASELINE config 5 -- ONE 8192x8192 image banded over the GPUs (strong scaling).
+    Host image in, every rank's rows of (segm, segm_soft) out; the time is the max over ranks."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback)'
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from pyimsegm_b200 import _lib, pipelines, tiled
+    lib = _lib.lib()
+    side = args.tiled_side
+    host_img = torch.from_numpy(synth_image(5, side, side)).pin_memory()
+    host_np = host_img.numpy()
+    comm = tiled.default_comm()
+
+    def step():
+        return tiled.pipe_color2d_slic_features_model_graphcut_tiled(host_np, NB_CLASSES, FEATURES, sp_size=SP_SIZE, sp_regul=SP_REGUL,
+                                                                     gc_regul=GC_REGUL, gc_edge_type='model', comm=comm)
+
+    def whole():
+        return pipelines.pipe_color2d_slic_features_model_graphcut(host_np, NB_CLASSES, FEATURES, sp_size=SP_SIZE, sp_regul=SP_REGUL,
+                                                                   gc_regul=GC_REGUL, gc_edge_type='model')
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(steps):
+            out = fn()
+        ev1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device='cuda', dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    keep = None
+    for _ in range(max(args.warmup, 3)):
+        keep = step()
+    del keep
+    lib.isb_profile_enable(1)
+    n0 = lib.isb_launch_count()
+    ms, (segm, soft, (lo, hi)) = timed(step, args.steps)
+    launches = lib.isb_launch_count() - n0
+    nstage = lib.isb_profile_stage_count()
+    ms_arr, cnt_arr = (C.c_double * nstage)(), (C.c_longlong * nstage)()
+    lib.isb_profile_collect(ms_arr, cnt_arr)
+    lib.isb_profile_enable(0)
+    stages = {lib.isb_profile_stage_name(i).decode(): {'ms_per_step': ms_arr[i] / args.steps, 'launches_per_step': cnt_arr[i] / args.steps}
+              for i in range(nstage)}
+    mono = None
+    if world == 1:
+        del segm, soft
+        for _ in range(2):
+            keep = whole()
+        del keep
+        ms_w, _ = timed(whole, args.steps)
+        mono = {'value': args.steps * side * side / 1e6 / (ms_w / 1e3), 'unit': 'MPix/s', 'ms_per_step': ms_w / args.steps,
+                'note': 'the same image through the single-GPU API (pipe_color2d_slic_features_model_graphcut)'}
+    if rank == 0:
+        value = args.steps * side * side / 1e6 / (ms / 1e3)
+        line = {'metric': METRIC, 'value': value, 'unit': 'MPix/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+                'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+                'data': 'synthetic',
+                'config': {'workload': 'config5: ONE %dx%d RGB f64 synthetic image banded over %d GPU(s), sp_size=29, colour-mean, '
+                                       '3-class GMM + GraphCut' % (side, side, world),
+                           'parallelism': 'row bands; per sweep one all_reduce of 6 int64 per cluster; label map broadcast; graph cut replicated',
+                           'timed': 'host image in (pinned), the rank\'s rows of segm + segm_soft out (end to end; there is no resident variant)'},
+                'e2e': {'value': value, 'unit': 'MPix/s', 'ms_per_step': ms / args.steps,
+                        'h2d_bytes_per_step': int(host_np.nbytes // world), 'd2h_bytes_per_step': int((hi - lo) * side * (4 + 8 * NB_CLASSES))},
+                'gpu_launches': int(launches), 'stages': stages, 'whole_image_single_gpu': mono}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -304,9 +386,14 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-images', type=int, default=4, help='images in the bounded cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='config2', choices=['config2', 'config5'],
+                    help='config2 = the headline line (default); config5 = one 8192x8192 image banded over the GPUs (extra)')
+    ap.add_argument('--tiled-side', type=int, default=8192)
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'config5':
+        run_tiled(args)
     else:
         run_ours(args)
 

@@ -44,6 +44,7 @@ struct KmState {
     int* bin_start;  // [nbins + 1]
     int* bin_fill;   // [nbins]
     int* bin_of;     // [n]
+    int* pack_done;  // [1] CTA counter of k_pack
     Cand* packed;    // [n] cluster records in bin order (what k_assign streams)
     double* packed_maxdc; // [n] SLICO: the maxima in bin order, beside `packed`
     unsigned long long* maxdc; // [n] SLICO colour-distance maxima as raw double bits (non-negative doubles order like their bits)
@@ -71,32 +72,33 @@ __device__ __forceinline__ int4 make_window(double cy, double cx, int step_y, in
     return w;
 }
 
-// single CTA.  first == 1: centres from the seed grid (colour part 0), windows, bin counts.  Then (always): exclusive scan
-// of the bin counts and the packed, bin-ordered cluster records that k_assign streams.  In the sweeps k_update has already
-// written centroids, windows, bin_of and counted the bins.
-__global__ void __launch_bounds__(1024) k_finalize_bin(KmState s, const double* seeds_yx, int first)
+// Between two sweeps the clusters are re-binned in three small launches:
+//   k_seed (first sweep only) or k_update / k_import : centres, windows, bin_of, and a count per bin in bin_fill
+//   k_scan_bins (one CTA)  : exclusive scan of the counts -> bin_start; the counts are zeroed (they become the fill cursors)
+//   k_pack (many CTAs)     : the packed, bin-ordered cluster records that k_assign streams; order inside a bin is irrelevant
+//   (k_assign leaves bin_fill alone; k_update / k_import need it zero again, k_pack's last CTA does that)
+__global__ void k_seed(KmState s, const double* __restrict__ seeds_yx)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= s.n) return;
+    const double cy = seeds_yx[2 * k], cx = seeds_yx[2 * k + 1];
+    s.cy[k] = cy; s.cx[k] = cx; s.c0[k] = 0.0; s.c1[k] = 0.0; s.c2[k] = 0.0;
+    s.win[k] = make_window(cy, cx, s.step_y, s.step_x, s.Hg, s.W);
+    const int by = min(max((int)cy / s.B, 0), s.nby - 1), bx = min(max((int)cx / s.B, 0), s.nbx - 1);
+    s.bin_of[k] = by * s.nbx + bx;
+    atomicAdd(&s.bin_fill[by * s.nbx + bx], 1);
+    s.obb[k] = make_int4(INT_MAX, -1, INT_MAX, -1);
+    s.maxdc[k] = (unsigned long long)__double_as_longlong(1.0);
+}
+
+__global__ void __launch_bounds__(1024) k_scan_bins(KmState s)
 {
     const int nbins = s.nby * s.nbx;
-    if (first) {
-        for (int b = threadIdx.x; b < nbins; b += blockDim.x) s.bin_fill[b] = 0;
-        __syncthreads();
-        for (int k = threadIdx.x; k < s.n; k += blockDim.x) {
-            const double cy = seeds_yx[2 * k], cx = seeds_yx[2 * k + 1];
-            s.cy[k] = cy; s.cx[k] = cx; s.c0[k] = 0.0; s.c1[k] = 0.0; s.c2[k] = 0.0;
-            s.win[k] = make_window(cy, cx, s.step_y, s.step_x, s.Hg, s.W);
-            const int by = min(max((int)cy / s.B, 0), s.nby - 1), bx = min(max((int)cx / s.B, 0), s.nbx - 1);
-            s.bin_of[k] = by * s.nbx + bx;
-            atomicAdd(&s.bin_fill[by * s.nbx + bx], 1);
-            s.obb[k] = make_int4(INT_MAX, -1, INT_MAX, -1);
-            s.maxdc[k] = (unsigned long long)__double_as_longlong(1.0);
-        }
-    }
-    __syncthreads();
     // exclusive scan of bin counts: warp shuffles + one partial per warp, chunks of blockDim
     __shared__ int s_wsum[32];
     __shared__ int s_part_total;
     __shared__ int s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
+    if (threadIdx.x == 0) { s_carry = 0; *s.pack_done = 0; }
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int base = 0; base < nbins; base += blockDim.x) {
@@ -122,20 +124,32 @@ __global__ void __launch_bounds__(1024) k_finalize_bin(KmState s, const double* 
         __syncthreads();
     }
     if (threadIdx.x == 0) s.bin_start[nbins] = s_carry;
-    __syncthreads();
-    for (int k = threadIdx.x; k < s.n; k += blockDim.x) {
-        int bin = s.bin_of[k];
-        if (bin < 0) continue;
-        const int pos = s.bin_start[bin] + atomicAdd(&s.bin_fill[bin], 1);
-        const int4 w = s.win[k];
-        Cand c;
-        c.cy = s.cy[k]; c.cx = s.cx[k]; c.c0 = s.c0[k]; c.c1 = s.c1[k]; c.c2 = s.c2[k];
-        c.y0 = w.x; c.y1 = w.y; c.x0 = w.z; c.x1 = w.w; c.k = k; c.pad = 0;
-        s.packed[pos] = c;
-        if (s.slico) s.packed_maxdc[pos] = __longlong_as_double((long long)s.maxdc[k]);
+}
+
+__global__ void __launch_bounds__(256) k_pack(KmState s)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < s.n) {
+        const int bin = s.bin_of[k];
+        if (bin >= 0) {
+            const int pos = s.bin_start[bin] + atomicAdd(&s.bin_fill[bin], 1);
+            const int4 w = s.win[k];
+            Cand c;
+            c.cy = s.cy[k]; c.cx = s.cx[k]; c.c0 = s.c0[k]; c.c1 = s.c1[k]; c.c2 = s.c2[k];
+            c.y0 = w.x; c.y1 = w.y; c.x0 = w.z; c.x1 = w.w; c.k = k; c.pad = 0;
+            s.packed[pos] = c;
+            if (s.slico) s.packed_maxdc[pos] = __longlong_as_double((long long)s.maxdc[k]);
+        }
     }
+    // the last CTA to finish zeroes the fill cursors: k_update / k_import count the next sweep's bins from zero
+    __shared__ int s_last;
     __syncthreads();
-    for (int b = threadIdx.x; b < nbins; b += blockDim.x) s.bin_fill[b] = 0; // k_update counts the next sweep's bins from zero
+    if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(s.pack_done, 1) == (int)gridDim.x - 1; }
+    __syncthreads();
+    if (s_last) {
+        const int nbins = s.nby * s.nbx;
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x) s.bin_fill[b] = 0;
+    }
 }
 
 // non-negative doubles order like their bit patterns: compare on the integer pipe instead of the FP64 pipe
@@ -146,7 +160,7 @@ __device__ __forceinline__ unsigned long long dbits(double v) { return (unsigned
 // The tile's Lab values are staged in shared memory, candidates are visited nearest-first and the loop stops as soon as
 // the spatial lower bound of every remaining candidate exceeds the worst of the thread's current minima.
 template <bool SLICO>
-__global__ void __launch_bounds__(ATHREADS) k_assign(KmState s, const double* __restrict__ lab, int* __restrict__ labels)
+__global__ void __launch_bounds__(ATHREADS, 5) k_assign(KmState s, const double* __restrict__ lab, int* __restrict__ labels)
 {
     __shared__ Cand cand[ACAP];
     __shared__ double s_maxdc[SLICO ? ACAP : 1];
@@ -343,7 +357,7 @@ template <bool BAND>
 __global__ void __launch_bounds__(256) k_update(KmState s, const double* __restrict__ lab, const int* __restrict__ labels,
                                                 long long* __restrict__ xchg)
 {
-    __shared__ double buf[8][3][32];
+    __shared__ double buf[8][3][64];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int k = blockIdx.x * 8 + wl;
     if (k >= s.n) return;
@@ -364,37 +378,69 @@ __global__ void __launch_bounds__(256) k_update(KmState s, const double* __restr
     const size_t HW = s.pstride;
     double acc = 0.0;
     long long cnt = 0, sy = 0, sx = 0;
-    // the box is walked in raster order, 32 pixels at a time; the label load of the next chunk is issued before the current
-    // chunk is processed (the loads are the latency that bounds this kernel)
+    // the box is walked in raster order, 32 pixels at a time.  The loads are the latency that bounds this kernel, so label AND
+    // colours of the chunks two ahead are requested (unconditionally: the box is ~2x the members, the extra reads hit L2)
+    // before the current chunk is compacted and added.
     const int nchunk = (x1 > x0) ? (x1 - x0 + 31) / 32 : 0;
     const int total = (y1 > y0) ? (y1 - y0) * nchunk : 0;
-    int y = y0, xb = x0;
-    int lab_next = -1;
-    if (total > 0) { const int x = xb + lane; lab_next = (x < x1) ? labels[(size_t)y * s.W + x] : -1; }
-    for (int it = 0; it < total; ++it) {
-        const int cy_ = y, cxb = xb;
-        const int lab_cur = lab_next;
-        xb += 32;
-        if (xb >= x1) { xb = x0; ++y; }
-        if (it + 1 < total) { const int x = xb + lane; lab_next = (x < x1) ? labels[(size_t)y * s.W + x] : -1; }
-        const int x = cxb + lane;
-        const bool m = lab_cur == k;
-        const unsigned mask = __ballot_sync(0xffffffffu, m);
-        if (!mask) continue;
-        const size_t rowp = (size_t)cy_ * s.W;
-        const int nm = __popc(mask);
-        if (m) {
-            int pos = __popc(mask & ((1u << lane) - 1u));
-            buf[wl][0][pos] = lab[rowp + x];
-            buf[wl][1][pos] = lab[HW + rowp + x];
-            buf[wl][2][pos] = lab[2 * HW + rowp + x];
-            sx += x;
+    int ly = y0, lxb = x0;   // load cursor
+    int cy_ = y0, cxb = x0;  // consume cursor
+    int Lq[2];
+    double Vq[2][3];
+    auto issue = [&](int sl, bool valid) {
+        const int x = lxb + lane;
+        Lq[sl] = -1;
+        if (valid && x < x1) {
+            const size_t p = (size_t)ly * s.W + x;
+            Lq[sl] = labels[p];
+            Vq[sl][0] = lab[p]; Vq[sl][1] = lab[HW + p]; Vq[sl][2] = lab[2 * HW + p];
+        }
+        lxb += 32;
+        if (lxb >= x1) { lxb = x0; ++ly; }
+    };
+    issue(0, total > 0);
+    issue(1, total > 1);
+    for (int it = 0; it < total; it += 2) {
+        // two consecutive chunks per round: one compaction, one pair of warp barriers, one run of adds
+        const bool two = it + 1 < total;
+        const int l0 = Lq[0], l1 = two ? Lq[1] : -1;
+        const double a0_ = Vq[0][0], a1_ = Vq[0][1], a2_ = Vq[0][2];
+        const double b0_ = Vq[1][0], b1_ = Vq[1][1], b2_ = Vq[1][2];
+        const int ya = cy_, xa = cxb + lane;
+        cxb += 32;
+        if (cxb >= x1) { cxb = x0; ++cy_; }
+        const int yb = cy_, xb_ = cxb + lane;
+        cxb += 32;
+        if (cxb >= x1) { cxb = x0; ++cy_; }
+        issue(0, it + 2 < total);
+        issue(1, it + 3 < total);
+        const bool m0 = l0 == k, m1 = l1 == k;
+        const unsigned mask0 = __ballot_sync(0xffffffffu, m0), mask1 = __ballot_sync(0xffffffffu, m1);
+        if (!(mask0 | mask1)) continue;
+        const int nm0 = __popc(mask0), nm1 = __popc(mask1), nm = nm0 + nm1;
+        const unsigned below = (1u << lane) - 1u;
+        if (m0) {
+            const int pos = __popc(mask0 & below);
+            buf[wl][0][pos] = a0_; buf[wl][1][pos] = a1_; buf[wl][2][pos] = a2_;
+            sx += xa;
+        }
+        if (m1) {
+            const int pos = nm0 + __popc(mask1 & below);
+            buf[wl][0][pos] = b0_; buf[wl][1][pos] = b1_; buf[wl][2][pos] = b2_;
+            sx += xb_;
         }
         cnt += nm;
-        sy += (long long)(cy_ + s.y_off) * nm;
+        sy += (long long)(ya + s.y_off) * nm0 + (long long)(yb + s.y_off) * nm1;
         __syncwarp();
-        if (lane < 3)
-            for (int i = 0; i < nm; ++i) acc = __dadd_rn(acc, buf[wl][lane][i]);
+        if (lane < 3) {
+            const double* bsrc = buf[wl][lane];
+            int i = 0;
+            for (; i + 4 <= nm; i += 4) {
+                const double d0 = bsrc[i], d1 = bsrc[i + 1], d2 = bsrc[i + 2], d3 = bsrc[i + 3];
+                acc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc, d0), d1), d2), d3);
+            }
+            for (; i < nm; ++i) acc = __dadd_rn(acc, bsrc[i]);
+        }
         __syncwarp();
     }
 #pragma unroll
@@ -497,10 +543,26 @@ static size_t carve(KmState& s, void* ws, size_t bytes, int H, int W, int n, int
     s.bin_start = c.take<int>((size_t)s.nby * s.nbx + 1);
     s.bin_fill = c.take<int>((size_t)s.nby * s.nbx);
     s.bin_of = c.take<int>(n);
+    s.pack_done = c.take<int>(1);
     s.packed = c.take<Cand>(n);
     s.maxdc = c.take<unsigned long long>(n);
     s.packed_maxdc = c.take<double>(n);
     return isb_align(c.off);
+}
+
+// seeds != nullptr: first binning (centres from the seed grid); else re-binning after k_update / k_import
+static int rebin(KmState& s, const double* seeds_yx, cudaStream_t st)
+{
+    if (seeds_yx) {
+        ISB_CUDA_CHECK(cudaMemsetAsync(s.bin_fill, 0, sizeof(int) * (size_t)s.nby * s.nbx, st));
+        k_seed<<<(s.n + 255) / 256, 256, 0, st>>>(s, seeds_yx);
+        ISB_LAUNCH_CHECK();
+    }
+    k_scan_bins<<<1, 1024, 0, st>>>(s);
+    ISB_LAUNCH_CHECK();
+    k_pack<<<(s.n + 255) / 256, 256, 0, st>>>(s);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
 }
 
 } // namespace
@@ -524,8 +586,7 @@ extern "C" int isb_slic_kmeans(const double* lab_planar, int H, int W, const dou
     s.slico = slic_zero ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     ISB_CUDA_CHECK(cudaMemsetAsync(labels, 0, sizeof(int32_t) * (size_t)H * W, st));
-    k_finalize_bin<<<1, 1024, 0, st>>>(s, seeds_yx, 1);
-    ISB_LAUNCH_CHECK();
+    if (int rc = rebin(s, seeds_yx, st)) return rc;
     dim3 agrid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE);
     for (int it = 0; it < max_iter; ++it) {
         {
@@ -541,8 +602,7 @@ extern "C" int isb_slic_kmeans(const double* lab_planar, int H, int W, const dou
             k_slico_max<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(s, lab_planar, labels);
             ISB_LAUNCH_CHECK();
         }
-        { ProfScope p(ISB_PROF_FINALIZE, st); k_finalize_bin<<<1, 1024, 0, st>>>(s, seeds_yx, 0); }
-        ISB_LAUNCH_CHECK();
+        { ProfScope p(ISB_PROF_FINALIZE, st); if (int rc = rebin(s, nullptr, st)) return rc; }
     }
     if (centroids) {
         k_export_centroids<<<(n_seeds + 255) / 256, 256, 0, st>>>(s, centroids);
@@ -586,9 +646,7 @@ extern "C" int isb_slic_band_begin(const isb_slic_band_t* b, isb_stream_t stream
     if (int rc = band_state(b, s)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     ISB_CUDA_CHECK(cudaMemsetAsync(b->labels_slab, 0, sizeof(int32_t) * (size_t)b->slab_rows * b->width, st));
-    k_finalize_bin<<<1, 1024, 0, st>>>(s, b->seeds_yx, 1);
-    ISB_LAUNCH_CHECK();
-    return ISB_OK;
+    return rebin(s, b->seeds_yx, st);
 }
 
 extern "C" int isb_slic_band_assign(const isb_slic_band_t* b, isb_stream_t stream)
@@ -644,7 +702,5 @@ extern "C" int isb_slic_band_finalize(const isb_slic_band_t* b, const uint64_t* 
         ISB_CUDA_CHECK(cudaMemcpyAsync(s.maxdc, maxdc_xchg, sizeof(uint64_t) * (size_t)s.n, cudaMemcpyDeviceToDevice, st));
     }
     ProfScope p(ISB_PROF_FINALIZE, st);
-    k_finalize_bin<<<1, 1024, 0, st>>>(s, b->seeds_yx, 0);
-    ISB_LAUNCH_CHECK();
-    return ISB_OK;
+    return rebin(s, nullptr, st);
 }
