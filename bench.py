@@ -58,6 +58,16 @@ def load_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
+def load_traffic():
+    """DRAM bytes per k_assign launch from the committed `ncu --set full` capture (profiles/), or None"""
+    path = os.path.join(ROOT, 'profiles', 'r01d_assign_traffic.json')
+    try:
+        with open(path) as f:
+            return int(json.load(f)['traffic_bytes_per_launch'])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons DURING the timed region"""
     QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
@@ -281,7 +291,7 @@ def run_ours(args):
                       'note': 'segment_images_batch: same host-in/host-out path, copies of consecutive images overlapped on 2 streams'},
         'gpu_launches': int(launches),
         'roofline': {'kernel': 'k_assign (slic_assign)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                     'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                     'frac': achieved / peak, 'traffic': load_traffic(), 'traffic_source': 'profiles/r01d_ncu_top_kernels.md', 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': ASSIGN_BYTES_PER_PX * H * W, 'launch_ms': t_assign * 1e3},
         'stages': stages,
         'clocks': clocks,
