@@ -6,9 +6,9 @@ Modules of the reference outside that path (classification, region_growing, anno
 import sys
 
 import pyimsegm_b200
-from pyimsegm_b200 import descriptors, graph_cuts, labeling, pipelines, superpixels, utilities
+from pyimsegm_b200 import descriptors, graph_cuts, labeling, pipelines, superpixels, tiled, utilities
 
-for _name in ('descriptors', 'graph_cuts', 'labeling', 'pipelines', 'superpixels', 'utilities'):
+for _name in ('descriptors', 'graph_cuts', 'labeling', 'pipelines', 'superpixels', 'tiled', 'utilities'):
     sys.modules[__name__ + '.' + _name] = getattr(pyimsegm_b200, _name)
 
 __version__ = '0.1.9+b200'
