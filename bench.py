@@ -49,6 +49,27 @@ def synth_image(seed, h=H, w=W, n_classes=NB_CLASSES, cell=64):
     return np.clip(img + rng.normal(0, 0.05, img.shape), 0, 1)
 
 
+def synth_texture_image(seed, h=H, w=W, n_classes=4, cell=64):
+    """config-3 style image: Voronoi regions of 4 classes, each class with its own mean and a sinusoidal
+    texture of period 4 / 8 / 16 / 32 px in a random orientation, gaussian noise"""
+    rng = np.random.RandomState(seed)
+    pts = rng.rand(40, 2) * [h, w]
+    cls = rng.randint(0, n_classes, 40)
+    gy, gx = np.mgrid[:(h + cell - 1) // cell, :(w + cell - 1) // cell] * cell + cell / 2
+    near = ((gy[..., None] - pts[:, 0]) ** 2 + (gx[..., None] - pts[:, 1]) ** 2).argmin(-1)
+    cl = np.kron(cls[near], np.ones((cell, cell), dtype=int))[:h, :w]
+    yy, xx = np.mgrid[:h, :w].astype(np.float64)
+    img = np.zeros((h, w))
+    means = np.linspace(0.3, 0.7, n_classes)
+    for c in range(n_classes):
+        ang = rng.rand() * np.pi
+        period = 4.0 * 2 ** c
+        wave = 0.12 * np.sin(2 * np.pi * (np.cos(ang) * xx + np.sin(ang) * yy) / period)
+        img = np.where(cl == c, means[c] + wave, img)
+    img = img[..., None] + np.array([0.0, 0.03, -0.03])
+    return np.clip(img + rng.normal(0, 0.03, img.shape), 0, 1)
+
+
 def load_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.isfile(path):
@@ -388,6 +409,85 @@ def run_tiled(args):
         dist.destroy_process_group()
 
 
+def run_texture(args):
+    """extra workload (not the headline line): BASELINE config 3 -- 2048x2048 images with the full Leung-Malik bank + colour
+    statistics (D = 189), 4 classes, images sharded over the GPUs (weak scaling; the 64-image batch is steps x GPUs images).
+    With D = 189 the class model is scikit-learn on the host, exactly as in the reference (the device GMM covers D <= 16)."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback)'
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from pyimsegm_b200 import _lib, pipelines
+    lib = _lib.lib()
+    fts = {'color': ('mean', 'std', 'energy'), 'tLM': ('mean', 'std', 'energy')}
+    host_np = torch.from_numpy(synth_texture_image(3000 + rank)).pin_memory().numpy()
+
+    def features_only():
+        return pipelines.compute_color2d_superpixels_features(host_np, fts, sp_size=SP_SIZE, sp_regul=SP_REGUL)
+
+    def step():
+        return pipelines.pipe_color2d_slic_features_model_graphcut(host_np, 4, fts, sp_size=SP_SIZE, sp_regul=SP_REGUL,
+                                                                   gc_regul=GC_REGUL, gc_edge_type='model')
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(steps):
+            out = fn()
+        ev1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = torch.tensor([max(ev0.elapsed_time(ev1), wall)], device='cuda', dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        features_only()
+    step()
+    lib.isb_profile_enable(1)
+    ms_f, (slic, feats) = timed(features_only, args.steps)
+    nstage = lib.isb_profile_stage_count()
+    ms_arr, cnt_arr = (C.c_double * nstage)(), (C.c_longlong * nstage)()
+    lib.isb_profile_collect(ms_arr, cnt_arr)
+    lib.isb_profile_enable(0)
+    n0 = lib.isb_launch_count()
+    ms, (segm, soft) = timed(step, args.steps)
+    launches = lib.isb_launch_count() - n0
+    stages = {lib.isb_profile_stage_name(i).decode(): {'ms_per_step': ms_arr[i] / args.steps} for i in range(nstage) if ms_arr[i] > 0}
+    if rank == 0:
+        mpix = H * W / 1e6
+        lm = stages.get('lm_texture', {}).get('ms_per_step', 0.0)
+        line = {'metric': METRIC, 'value': world * args.steps * mpix / (ms / 1e3), 'unit': 'MPix/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f64 (SLIC, statistics), tf32x3 with f32 accumulate (LM bank)', 'data': 'synthetic',
+                'config': {'workload': 'config3: 2048x2048 RGB f64 textured synthetic, colour + full LM bank (D=%d), 4-class GMM + GraphCut; '
+                                       '1 image per GPU per step' % feats.shape[1],
+                           'class_model': 'scikit-learn GaussianMixture on the host (D > 16), as the reference',
+                           'timed': 'host image in, (segm, segm_soft) out, wall clock >= CUDA events (host model fit inside)'},
+                'e2e': {'value': world * args.steps * mpix / (ms / 1e3), 'unit': 'MPix/s', 'h2d_bytes_per_step': int(host_np.nbytes),
+                        'd2h_bytes_per_step': int(segm.nbytes + soft.nbytes)},
+                'features_only': {'value': world * args.steps * mpix / (ms_f / 1e3), 'unit': 'MPix/s', 'ms_per_step': ms_f / args.steps,
+                                  'note': 'compute_color2d_superpixels_features: SLIC + colour + LM descriptors, host in / host out'},
+                'roofline': {'kernel': 'k_lm_conv (lm_texture)', 'bound': 'tensor', 'unit': 'TFLOP/s',
+                             'achieved': 3 * 76 * 33 * 33 * 2 * H * W / (lm / 1e3) / 1e12 if lm > 0 else None,
+                             'note': 'algorithmic flops (one multiply-add per tap); the kernel executes 3 TF32 MMAs per product. '
+                                     'The stage time also holds the sigma-150 background pass; see profiles/r01_lm_texture.md'},
+                'gpu_launches': int(launches), 'stages': stages}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -396,7 +496,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-images', type=int, default=4, help='images in the bounded cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--workload', default='config2', choices=['config2', 'config5'],
+    ap.add_argument('--workload', default='config2', choices=['config2', 'config3', 'config5'],
                     help='config2 = the headline line (default); config5 = one 8192x8192 image banded over the GPUs (extra)')
     ap.add_argument('--tiled-side', type=int, default=8192)
     args = ap.parse_args()
@@ -404,6 +504,8 @@ def main():
         run_reference(args)
     elif args.workload == 'config5':
         run_tiled(args)
+    elif args.workload == 'config3':
+        run_texture(args)
     else:
         run_ours(args)
 

@@ -31,7 +31,8 @@ MIN_MAX_EDGE_WEIGHT = 1e3
 USE_DEVICE_GMM = True
 #: seed of the device k-means++ initialisation (the reference leaves its model unseeded)
 RANDOM_SEED = 0
-DEVICE_GMM_MAX_FEATURES, DEVICE_GMM_MAX_CLASSES = 16, 8
+#: D <= 16 runs as one kernel (a CTA per restart), 16 < D <= 256 (colour + Leung-Malik = 189) as batched FP64 GEMMs
+DEVICE_GMM_MAX_FEATURES, DEVICE_GMM_MAX_CLASSES = 256, 8
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -221,6 +221,43 @@ def test_device_gmm_matches_sklearn_from_shared_start():
     assert purity > 0.98
 
 
+@pytest.mark.parametrize('D,K', [(40, 3), (189, 4)])
+def test_device_gmm_large_d_matches_sklearn_from_shared_start(D, K):
+    """the large-D path of the device class model (batched FP64 GEMMs + Cholesky; colour + Leung-Malik features give
+    D = 189): same EM as sklearn from the same hard start, tolerance 1e-6 as for the small path"""
+    from sklearn import mixture, preprocessing
+    from pyimsegm_b200 import graph_cuts as gc
+    rng = np.random.RandomState(D)
+    sizes = (700, 900, 600, 800)[:K]
+    centers = rng.normal(0, 1.0, (K, D))
+    mix = rng.normal(0, 0.3, (K, D, D)) / np.sqrt(D)
+    X = np.concatenate([c + rng.normal(0, 1.0, (n, D)) @ (np.eye(D) * 0.4 + m) for c, m, n in zip(centers, mix, sizes)])
+    truth = np.repeat(np.arange(K), sizes)
+    y0 = truth.copy()
+    flip = rng.rand(len(X)) < 0.3
+    y0[flip] = rng.randint(0, K, flip.sum())       # a 70 % informed start so that EM has real work to do
+    model = gc.estim_class_model_device(X, K, use_scaler=True, max_iter=99, init_labels=y0)
+    gmm = model.named_steps['model']
+    Z = preprocessing.StandardScaler().fit(X).transform(X)
+    resp = np.eye(K)[y0]
+    nk = resp.sum(0) + 10 * np.finfo(float).eps
+    means0 = resp.T @ Z / nk[:, None]
+    covs0 = np.array([((resp[:, k, None] * (Z - means0[k])).T @ (Z - means0[k])) / nk[k] + 1e-6 * np.eye(D) for k in range(K)])
+    ref = mixture.GaussianMixture(K, covariance_type='full', max_iter=99, n_init=1, weights_init=nk / len(Z), means_init=means0,
+                                  precisions_init=np.linalg.inv(covs0)).fit(Z)
+    assert gmm.n_iter_ == ref.n_iter_ and gmm.converged_ == ref.converged_
+    np.testing.assert_allclose(gmm.weights_, ref.weights_, rtol=1e-6)
+    np.testing.assert_allclose(gmm.means_, ref.means_, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(gmm.covariances_, ref.covariances_, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(gmm.lower_bound_, ref.lower_bound_, rtol=1e-8)
+    np.testing.assert_allclose(gmm.precisions_cholesky_, ref.precisions_cholesky_, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(model.predict_proba(X), ref.predict_proba(Z), rtol=1e-5, atol=1e-9)
+    # unseeded default (k-means++ on the device, 9 restarts): must recover the blobs
+    lab = gc.estim_class_model(X, K).predict_proba(X).argmax(1)
+    purity = sum(np.bincount(lab[truth == k], minlength=K).max() for k in range(K)) / len(X)
+    assert purity > 0.97
+
+
 def test_fully_resident_pipeline_is_consistent(oracle):
     """pipe_color2d_slic_features_model_graphcut with the device-fitted GMM: its own model, replayed through the
     shared-model entry point and through the oracle, must give the identical label map"""
