@@ -13,12 +13,17 @@
 // N is tiny (superpixels, not pixels): this stage is latency bound, it exists to remove the host sync.
 #include "common.cuh"
 #include <float.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
 constexpr int GT = 512;      // threads per restart CTA
 constexpr int DMAX = 16;     // feature dimensions of the single-kernel path (one CTA per restart, everything on chip)
-constexpr int DBIG = 256;    // feature dimensions of the large-D path (batched GEMMs, e.g. colour + Leung-Malik = 189)
+constexpr int CLI = 8;       // CTAs per restart (one thread-block cluster) in the large-D initialisation
+constexpr int KS = 8;        // split-K factor of the M-step Gram matrices
+constexpr int DBIG = 232;    // feature dimensions of the large-D path (batched GEMMs, e.g. colour + Leung-Malik = 189); the packed
+                             // lower triangle of one covariance (D (D + 1) / 2 doubles) has to fit the shared memory of a CTA
 constexpr int KMAX = 8;      // mixture components handled on the device
 
 struct GmmWs {
@@ -33,7 +38,10 @@ struct GmmWs {
     double* bvec;     // [n_init, K, D]     mu U
     double* ldw;      // [n_init, K]        log|prec_chol| + log weight
     double* lowpart;  // [n_init, ceil(N / 8)] per-block sums of the log-likelihood
-    double* cent;     // [n_init, K, D]     k-means centres
+    double* cent;     // [n_init, 2, K, D]  k-means centres (double buffered)
+    int* iflag;       // [n_init, CLI]      "a label changed" per CTA of the init cluster
+    double* gram;     // [n_init, K, KS, D, D] split-K partial Gram matrices of the M-step
+    double* sresp;    // [n_init, N, K]     sqrt(resp), the weights of the M-step Gram matrices
     double* tot;      // [n_init, K, 1 + D] k-means counts / coordinate sums
     double* state;    // [n_init, 4]        lower bound of the previous E-step, done, -, failed
     int* flag;        // [1]                restarts still running
@@ -371,43 +379,72 @@ constexpr int TM = 64, TN = 64, TK = 16;
 // C[b] (M x Nn) = op(A[b]) B[b], row-major; TRANS_A: A[b] is stored Kd x M.  The sample count may come from the device (n_dev).
 // Batch b = (restart r, component k) = (b / per, b % per); operand X of the batch starts at X + r * strideXr + k * strideXk.
 // A batch whose restart is done is skipped.
-struct BatchStride { size_t ar, ak, br, bk, cr, ck; };
-template <bool TRANS_A>
+struct BatchStride { size_t ar, ak, br, bk, cr, ck, cs; };
+// ksplit > 1: the contraction index is cut into ksplit ranges, range s of batch b is blockIdx.z = b * ksplit + s and writes its
+// partial product at C + ... + s * cs (the consumer adds the partials in order).  The next tile's global loads are issued before
+// the current tile is multiplied.
+// FUSE_W (with TRANS_A, the M-step): A and B are both the standardised features X [Kd x D]; element (n, m) is taken as
+// sr[n] (X[n][m] - mu[m]) with sr = sqrt(resp) of the batch's (restart, component) -- the weighted, centred copy is never stored.
+// b_upper: B[b] is upper triangular, so columns n0.. only need the rows below n0 + TN.
+struct FuseW { const double* sresp; const double* mu; size_t sr_r; int K; size_t mu_r; int D; };
+template <bool TRANS_A, bool FUSE_W>
 __global__ void __launch_bounds__(256) k_dgemm_batched(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
                                                        double* __restrict__ C, int ldc, BatchStride bs, int M_in, int Nn, int Kd_in,
-                                                       const int* n_dev, int n_is_m, const double* state, int per)
+                                                       const int* n_dev, int n_is_m, const double* state, int per, int upper_only, int ksplit,
+                                                       int b_upper, FuseW fw)
 {
     __shared__ double As[TK][TM + 4];
     __shared__ double Bs[TK][TN + 4];
-    const int b = blockIdx.z, br = b / per, bk = b % per;
-    if (state[(size_t)br * 4 + 1] != 0.0) return;
+    const int b = blockIdx.z / ksplit, split = blockIdx.z % ksplit, br = b / per, bk = b % per;
+    if (state && state[(size_t)br * 4 + 1] != 0.0) return;
+    if (upper_only && blockIdx.x < blockIdx.y) return;   // symmetric result: tiles below the diagonal are not needed
     const int nlim = n_dev ? *n_dev : 0x7fffffff;
     const int M = n_is_m ? min(M_in, nlim) : M_in;       // the sample count is M (E-step) or Kd (M-step)
     const int Kd = n_is_m ? Kd_in : min(Kd_in, nlim);
     const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
     if (m0 >= M) return;
-    A += br * bs.ar + bk * bs.ak; B += br * bs.br + bk * bs.bk; C += br * bs.cr + bk * bs.ck;
+    A += br * bs.ar + bk * bs.ak; B += br * bs.br + bk * bs.bk; C += br * bs.cr + bk * bs.ck + split * bs.cs;
+    const int tiles = (Kd + TK - 1) / TK, tper = (tiles + ksplit - 1) / ksplit;
+    const int k_begin = split * tper * TK;
+    int k_end = min(Kd, (split + 1) * tper * TK);
+    if (b_upper) k_end = min(k_end, n0 + TN);
+    const double* sr = FUSE_W ? fw.sresp + br * fw.sr_r + bk : nullptr;          // sr[n * K]
+    const double* mu = FUSE_W ? fw.mu + br * fw.mu_r + (size_t)bk * fw.D : nullptr;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    for (int k0 = 0; k0 < Kd; k0 += TK) {
-        for (int i = threadIdx.x; i < TK * TM; i += 256) {
+    double ra[4], rb[4];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = threadIdx.x + q * 256;
             int kk, mm;
             if (TRANS_A) { kk = i / TM; mm = i % TM; } else { mm = i / TK; kk = i % TK; }
             const int gm = m0 + mm, gk = k0 + kk;
-            double v = 0.0;
-            if (gm < M && gk < Kd) v = TRANS_A ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
-            As[kk][mm] = v;
+            ra[q] = (gm < M && gk < k_end) ? (TRANS_A ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk]) : 0.0;
+            const int kb = i / TN, nn = i % TN;
+            const int gkb = k0 + kb, gn = n0 + nn;
+            rb[q] = (gkb < k_end && gn < Nn) ? B[(size_t)gkb * ldb + gn] : 0.0;
+            if (FUSE_W) {   // TRANS_A: kk == kb (TM == TN), one weight for both operands
+                const double wgt = gk < k_end ? sr[(size_t)gk * fw.K] : 0.0;
+                ra[q] = (gm < M && gk < k_end) ? wgt * (ra[q] - mu[gm]) : 0.0;
+                rb[q] = (gkb < k_end && gn < Nn) ? wgt * (rb[q] - mu[gn]) : 0.0;
+            }
         }
-        for (int i = threadIdx.x; i < TK * TN; i += 256) {
-            const int kk = i / TN, nn = i % TN;
-            const int gk = k0 + kk, gn = n0 + nn;
-            Bs[kk][nn] = (gk < Kd && gn < Nn) ? B[(size_t)gk * ldb + gn] : 0.0;
+    };
+    if (k_begin < k_end) gload(k_begin);
+    for (int k0 = k_begin; k0 < k_end; k0 += TK) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = threadIdx.x + q * 256;
+            if (TRANS_A) As[i / TM][i % TM] = ra[q]; else As[i % TK][i / TK] = ra[q];
+            Bs[i / TN][i % TN] = rb[q];
         }
         __syncthreads();
+        if (k0 + TK < k_end) gload(k0 + TK);
 #pragma unroll
         for (int kk = 0; kk < TK; ++kk) {
             double a[4], bb[4];
@@ -432,108 +469,177 @@ __global__ void __launch_bounds__(256) k_dgemm_batched(const double* __restrict_
     }
 }
 
-// initial hard assignment of every restart: supplied labels, or k-means++ / Lloyd (as k_gmm_fit, centres in global memory)
-__global__ void __launch_bounds__(GT) k_big_init(int N_in, const int* n_dev, int D, int K, unsigned long long seed,
-                                                const int* __restrict__ init_labels, GmmWs w)
+// StandardScaler for many features: one CTA per 32 features, warps over the samples, lanes over the features; per-warp partials
+// are added in warp order (k_gmm_scale walks the features one by one -- fine for D <= 16, 2.4 ms at D = 189)
+__global__ void __launch_bounds__(1024) k_big_scale(const double* __restrict__ feat, int N_in, const int* n_dev, int D, int ld, int use_scaler,
+                                                   GmmWs w)
 {
+    __shared__ double s_acc[32][33];
+    __shared__ double s_mean[32], s_scale[32];
+    const int N = n_dev ? min(*n_dev, N_in) : N_in;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int d = blockIdx.x * 32 + lane;
+    double a = 0;
+    if (d < D) for (int n = wid; n < N; n += 32) a += feat[(size_t)n * ld + d];
+    s_acc[wid][lane] = a;
+    __syncthreads();
+    if (wid == 0) { double t = 0; for (int i = 0; i < 32; ++i) t += s_acc[i][lane]; s_mean[lane] = t / N; }
+    __syncthreads();
+    const double mean = s_mean[lane];
+    a = 0;
+    if (d < D) for (int n = wid; n < N; n += 32) { const double t = feat[(size_t)n * ld + d] - mean; a = fma(t, t, a); }
+    s_acc[wid][lane] = a;
+    __syncthreads();
+    if (wid == 0) {
+        double t = 0;
+        for (int i = 0; i < 32; ++i) t += s_acc[i][lane];
+        const double var = t / N;
+        double sc = sqrt(var), mu = mean;
+        const double ub = N * DBL_EPSILON * var + (N * mean * DBL_EPSILON) * (N * mean * DBL_EPSILON); // sklearn _is_constant_feature
+        if (var <= ub) sc = 1.0;
+        if (!use_scaler) { mu = 0.0; sc = 1.0; }
+        s_mean[lane] = mu; s_scale[lane] = sc;
+        if (d < D) { w.scale[d] = mu; w.scale[D + d] = sc; }
+    }
+    __syncthreads();
+    if (d < D) {
+        const double mu = s_mean[lane], sc = s_scale[lane];
+        for (int n = wid; n < N; n += 32) w.xs[(size_t)n * D + d] = (feat[(size_t)n * ld + d] - mu) / sc;
+    }
+}
+
+// initial hard assignment of every restart: supplied labels, or k-means++ / Lloyd as in k_gmm_fit.  One thread-block cluster of
+// CLI CTAs per restart; samples are spread over all warps of the cluster, the state (centres, labels, sums) lives in global
+// memory and cluster.sync() orders it.  Every CTA draws the same random numbers, so the control flow is identical in all of them.
+__global__ void __cluster_dims__(CLI, 1, 1) __launch_bounds__(GT) k_big_init(int N_in, const int* n_dev, int D, int K, unsigned long long seed,
+                                                                          const int* __restrict__ init_labels, GmmWs w)
+{
+    cg::cluster_group cl = cg::this_cluster();
     __shared__ double s_part[GT];
     __shared__ double s_red[GT / 32];
+    __shared__ double s_acc[GT / 32][33];
     __shared__ int s_pick;
-    __shared__ double s_shift;
     const int N = n_dev ? min(*n_dev, N_in) : N_in;
-    const int init = blockIdx.x;
+    const int init = blockIdx.x / CLI, rank = (int)cl.block_rank();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = GT / 32;
+    const int gw = rank * nw + wid, gnw = CLI * nw;          // warp index / warp count inside the restart
+    const int gt = rank * GT + threadIdx.x, gnt = CLI * GT;  // thread index / thread count inside the restart
     const double* xs = w.xs;
     double* resp = w.resp + (size_t)init * N_in * K;
     int* lab = w.lab + (size_t)init * N_in;
-    double* cent = w.cent + (size_t)init * K * D;
+    double* cent = w.cent + (size_t)init * 2 * K * D;
     double* tot = w.tot + (size_t)init * K * (1 + D);
-    if (threadIdx.x == 0) { w.state[init * 4] = -DBL_MAX; w.state[init * 4 + 1] = 0.0; w.state[init * 4 + 2] = 0.0; w.state[init * 4 + 3] = 0.0; }
+    int* chg = w.iflag + init * CLI;
+    if (gt == 0) { w.state[init * 4] = -DBL_MAX; w.state[init * 4 + 1] = 0.0; w.state[init * 4 + 2] = 0.0; w.state[init * 4 + 3] = 0.0; }
     if (init_labels) {
-        for (int n = threadIdx.x; n < N; n += GT) lab[n] = init_labels[(size_t)init * N_in + n];
-        __syncthreads();
+        for (int n = gt; n < N; n += gnt) lab[n] = init_labels[(size_t)init * N_in + n];
     } else {
         Rng rng(seed * 0x100000001B3ull + 1469598103934665603ull * (unsigned long long)(init + 1));
         double* d2 = w.red + (size_t)init * (N_in > GT ? N_in : GT);
         int first = (int)(rng.uniform() * N); if (first >= N) first = N - 1;
-        for (int d = threadIdx.x; d < D; d += GT) cent[d] = xs[(size_t)first * D + d];
-        __syncthreads();
-        for (int c = 1; c <= K; ++c) {
-            double loc = 0;
-            for (int n = threadIdx.x; n < N; n += GT) {
-                double s = 0;
-                for (int d = 0; d < D; ++d) { double t = xs[(size_t)n * D + d] - cent[(c - 1) * D + d]; s += t * t; }
-                double cur = (c == 1) ? s : fmin(d2[n], s);
-                d2[n] = cur;
-                loc += cur;
+        if (rank == 0) for (int d = threadIdx.x; d < D; d += GT) cent[d] = xs[(size_t)first * D + d];
+        cl.sync();
+        // k-means++: one D^2-weighted draw per further centre
+        for (int c = 1; c < K; ++c) {
+            for (int n = gw; n < N; n += gnw) {
+                double sq = 0;
+                for (int d = lane; d < D; d += 32) { const double t = xs[(size_t)n * D + d] - cent[(c - 1) * D + d]; sq = fma(t, t, sq); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                if (lane == 0) d2[n] = (c == 1) ? sq : fmin(d2[n], sq);
             }
-            double total = block_sum_d(loc, s_red);
-            if (c == K) break;
-            const double thr = rng.uniform() * total;
-            const int chunk = (N + GT - 1) / GT, beg = threadIdx.x * chunk, end = min(beg + chunk, N);
-            double cs = 0;
-            for (int n = beg; n < end; ++n) cs += d2[n];
-            s_part[threadIdx.x] = cs;
-            if (threadIdx.x == 0) s_pick = N - 1;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double run = 0; int t = 0;
-                for (; t < GT; ++t) { if (run + s_part[t] >= thr) break; run += s_part[t]; }
-                if (t < GT) {
-                    int b2 = t * chunk, e2 = min(b2 + chunk, N), n = b2;
-                    for (; n < e2; ++n) { run += d2[n]; if (run >= thr) break; }
-                    s_pick = min(n, N - 1);
+            cl.sync();
+            const double u = rng.uniform();   // every CTA draws, so the generators stay in step
+            if (rank == 0) {
+                const int chunk = (N + GT - 1) / GT, beg = threadIdx.x * chunk, end = min(beg + chunk, N);
+                double cs = 0;
+                for (int n = beg; n < end; ++n) cs += d2[n];
+                s_part[threadIdx.x] = cs;
+                if (threadIdx.x == 0) s_pick = N - 1;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double total = 0;
+                    for (int t = 0; t < GT; ++t) total += s_part[t];
+                    const double thr = u * total;
+                    double run = 0; int t = 0;
+                    for (; t < GT; ++t) { if (run + s_part[t] >= thr) break; run += s_part[t]; }
+                    if (t < GT) {
+                        int b2 = t * chunk, e2 = min(b2 + chunk, N), n = b2;
+                        for (; n < e2; ++n) { run += d2[n]; if (run >= thr) break; }
+                        s_pick = min(n, N - 1);
+                    }
                 }
+                __syncthreads();
+                for (int d = threadIdx.x; d < D; d += GT) cent[c * D + d] = xs[(size_t)s_pick * D + d];
             }
-            __syncthreads();
-            for (int d = threadIdx.x; d < D; d += GT) cent[c * D + d] = xs[(size_t)s_pick * D + d];
-            __syncthreads();
+            cl.sync();
         }
-        for (int n = threadIdx.x; n < N; n += GT) lab[n] = -1;
-        const int Q = K * (1 + D);
+        // Lloyd iterations (sklearn KMeans: max_iter 300, tol 1e-4 * mean feature variance; X is standardised)
+        for (int n = gt; n < N; n += gnt) lab[n] = -1;
+        cl.sync();
+        int cur = 0;
+        const int nr = 1 + (D + 31) / 32;       // rounds per cluster: the count, then 32 features at a time
         for (int it = 0; it < 300; ++it) {
+            const double* cc = cent + (size_t)cur * K * D;
+            double* cn = cent + (size_t)(cur ^ 1) * K * D;
             int changed = 0;
-            for (int n = threadIdx.x; n < N; n += GT) {
+            for (int n = gw; n < N; n += gnw) {
                 double best = DBL_MAX; int bk = 0;
                 for (int k = 0; k < K; ++k) {
-                    double s = 0;
-                    for (int d = 0; d < D; ++d) { double t = xs[(size_t)n * D + d] - cent[k * D + d]; s += t * t; }
-                    if (s < best) { best = s; bk = k; }
+                    double sq = 0;
+                    for (int d = lane; d < D; d += 32) { const double t = xs[(size_t)n * D + d] - cc[k * D + d]; sq = fma(t, t, sq); }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    if (sq < best) { best = sq; bk = k; }
                 }
-                if (lab[n] != bk) { lab[n] = bk; changed = 1; }
+                if (lane == 0 && lab[n] != bk) { lab[n] = bk; changed = 1; }
             }
             changed = __syncthreads_or(changed);
-            for (int q = threadIdx.x; q < Q; q += GT) {
-                const int k = q / (1 + D), j = q % (1 + D);
+            if (threadIdx.x == 0) chg[rank] = changed;
+            cl.sync();
+            int any = 0;
+            for (int i = 0; i < CLI; ++i) any |= chg[i];
+            // counts and coordinate sums: (cluster k, round) pairs are dealt to the CTAs; inside a CTA warp w takes the samples
+            // w, w + nw, ..., the lanes take the features, per-warp partials are added in warp order
+            for (int p = rank; p < K * nr; p += CLI) {
+                const int k = p / nr, round = p % nr;
+                const int d = (round - 1) * 32 + lane;
                 double a = 0;
-                for (int n = 0; n < N; ++n)
-                    if (lab[n] == k) a += j == 0 ? 1.0 : xs[(size_t)n * D + j - 1];
-                tot[q] = a;
+                if (round == 0) { if (lane == 0) for (int n = wid; n < N; n += nw) a += lab[n] == k ? 1.0 : 0.0; }
+                else if (d < D) for (int n = wid; n < N; n += nw) if (lab[n] == k) a += xs[(size_t)n * D + d];
+                s_acc[wid][lane] = a;
+                __syncthreads();
+                if (wid == 0 && (round == 0 ? lane == 0 : d < D)) {
+                    double t = 0;
+                    for (int i = 0; i < nw; ++i) t += s_acc[i][lane];
+                    tot[k * (1 + D) + (round == 0 ? 0 : 1 + d)] = t;
+                }
+                __syncthreads();
             }
-            __syncthreads();
+            cl.sync();
+            // shift (every CTA computes the same number) and the next centres (written by CTA 0 into the other buffer)
             double sh = 0;
             for (int i = threadIdx.x; i < K * D; i += GT) {
                 const int k = i / D, d = i % D;
                 const double cnt = tot[k * (1 + D)];
-                if (cnt > 0) { const double t = tot[k * (1 + D) + 1 + d] / cnt - cent[i]; sh += t * t; }
+                double v = cc[i];
+                if (cnt > 0) { v = tot[k * (1 + D) + 1 + d] / cnt; const double t = v - cc[i]; sh += t * t; }
+                if (rank == 0) cn[i] = v;
             }
             sh = block_sum_d(sh, s_red);
-            if (threadIdx.x == 0) s_shift = sh;
-            __syncthreads();
-            for (int i = threadIdx.x; i < K * D; i += GT) {
-                const int k = i / D, d = i % D;
-                const double cnt = tot[k * (1 + D)];
-                if (cnt > 0) cent[i] = tot[k * (1 + D) + 1 + d] / cnt;
-            }
-            __syncthreads();
-            if (!changed || s_shift <= 1e-4) break;
+            cur ^= 1;
+            cl.sync();
+            if (!any || sh <= 1e-4) break;
         }
-        __syncthreads();
     }
-    for (int i = threadIdx.x; i < N * K; i += GT) resp[i] = (lab[i / K] == i % K) ? 1.0 : 0.0;
+    cl.sync();
+    double* sresp = w.sresp + (size_t)init * N_in * K;
+    for (int i = gt; i < N * K; i += gnt) { const double r = (lab[i / K] == i % K) ? 1.0 : 0.0; resp[i] = r; sresp[i] = r; }
 }
 
-// nk and means of every (restart, component): grid (K, n_init); thread per feature, samples in sequence
-__global__ void __launch_bounds__(256) k_big_means(int N_in, const int* n_dev, int D, int K, GmmWs w)
+// nk and means of every (restart, component): grid (K, n_init, ceil(D / 32)), 1024 threads.  Warp w takes the samples w, w + 32,
+// ...; its lanes 32 features; the 32 per-warp partials are added in warp order (the result does not depend on scheduling).
+__global__ void __launch_bounds__(1024) k_big_means(int N_in, const int* n_dev, int D, int K, GmmWs w)
 {
     const int k = blockIdx.x, init = blockIdx.y;
     if (w.state[init * 4 + 1] != 0.0) return;
@@ -541,119 +647,142 @@ __global__ void __launch_bounds__(256) k_big_means(int N_in, const int* n_dev, i
     const double* resp = w.resp + (size_t)init * N_in * K;
     double* par = w.par + (size_t)init * pstride(K, D);
     double* wts = par; double* mu = par + K;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ double s_acc[32][33];
     __shared__ double s_nk;
-    if (threadIdx.x == 0) {
+    {
         double t = 0;
-        for (int n = 0; n < N; ++n) t += resp[(size_t)n * K + k];
-        s_nk = t + 10 * DBL_EPSILON;
-        wts[k] = s_nk;   // nk; divided by N once the covariance has used it (k_big_chol)
+        for (int n = threadIdx.x; n < N; n += 1024) t += resp[(size_t)n * K + k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) s_acc[wid][0] = t;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = 0;
+            for (int i = 0; i < 32; ++i) a += s_acc[i][0];
+            s_nk = a + 10 * DBL_EPSILON;
+            if (blockIdx.z == 0) wts[k] = s_nk;   // nk; divided by N once the covariance has used it (k_big_chol)
+        }
+        __syncthreads();
     }
+    const int d = blockIdx.z * 32 + lane;
+    double a = 0;
+    if (d < D)
+        for (int n = wid; n < N; n += 32) a = fma(resp[(size_t)n * K + k], w.xs[(size_t)n * D + d], a);
+    s_acc[wid][lane] = a;
     __syncthreads();
-    for (int d = threadIdx.x; d < D; d += 256) {
-        double a = 0;
-        for (int n = 0; n < N; ++n) a = fma(resp[(size_t)n * K + k], w.xs[(size_t)n * D + d], a);
-        mu[k * D + d] = a / s_nk;
+    if (wid == 0 && d < D) {
+        double t = 0;
+        for (int i = 0; i < 32; ++i) t += s_acc[i][lane];
+        mu[k * D + d] = t / s_nk;
     }
 }
 
-// Xw[r,k][n][d] = sqrt(resp) (x - mu): grid (ceil(N*D/256), K, n_init)
-__global__ void __launch_bounds__(256) k_big_weighted(int N_in, const int* n_dev, int D, int K, GmmWs w)
-{
-    const int k = blockIdx.y, init = blockIdx.z;
-    if (w.state[init * 4 + 1] != 0.0) return;
-    const int N = n_dev ? min(*n_dev, N_in) : N_in;
-    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= (size_t)N * D) return;
-    const int n = (int)(i / D), d = (int)(i % D);
-    const double* mu = w.par + (size_t)init * pstride(K, D) + K;
-    const double r = w.resp[((size_t)init * N_in + n) * K + k];
-    w.big[(((size_t)init * K + k) * N_in) * D + i] = sqrt(r) * (w.xs[i] - mu[k * D + d]);
-}
-
-// per (restart, component): covariance from the raw Gram matrix, Cholesky, prec_chol = (L^-1)^T, log-determinant + log weight,
-// b = mu U.  One CTA of 1024 threads; the matrix lives in global memory (L2), __syncthreads orders the accesses.
+// per (restart, component): covariance from the split-K Gram partials, Cholesky, prec_chol = (L^-1)^T, log-determinant + log
+// weight, b = mu U.  One CTA of 1024 threads; L lives in shared memory as a packed lower triangle (row i at i (i + 1) / 2).
 __global__ void __launch_bounds__(1024) k_big_chol(int N_in, const int* n_dev, int D, int K, double reg, GmmWs w)
 {
+    extern __shared__ double Ls[];
     const int k = blockIdx.x, init = blockIdx.y;
     if (w.state[init * 4 + 1] != 0.0) return;
     const int N = n_dev ? min(*n_dev, N_in) : N_in;
     double* par = w.par + (size_t)init * pstride(K, D);
     double* wts = par; double* mu = par + K + (size_t)k * D;
-    double* Cm = par + K + K * D + (size_t)k * D * D;                       // in: raw Gram; out: covariance
-    double* U = par + K + K * D + (size_t)K * D * D + (size_t)k * D * D;   // out: prec_chol (upper); scratch: L (lower)
+    double* Cm = par + K + K * D + (size_t)k * D * D;                       // out: covariance
+    double* U = par + K + K * D + (size_t)K * D * D + (size_t)k * D * D;   // out: prec_chol (upper triangular)
+    const double* G = w.gram + ((size_t)init * K + k) * KS * D * D;
     const int T = blockDim.x, tid = threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5, nw = T >> 5;
     const double nk = wts[k];
     __shared__ int s_bad;
-    __shared__ double s_piv;
+    __shared__ double s_ld[32];
+    __shared__ double s_col[DBIG];
     if (tid == 0) s_bad = 0;
-    // covariance (symmetrised from the upper triangle of the Gram matrix) and a working copy L
+    // covariance: the Gram partials are added in split order; only tiles on or above the diagonal were computed, so (a, b) with
+    // a > b is read from (b, a)
     for (int i = tid; i < D * D; i += T) {
         const int a = i / D, b = i % D;
-        const double g = a <= b ? Cm[a * D + b] : Cm[b * D + a];
-        U[i] = g / nk + (a == b ? reg : 0.0);
+        const int src = a <= b ? a * D + b : b * D + a;
+        double g = 0;
+        for (int sp = 0; sp < KS; ++sp) g += G[(size_t)sp * D * D + src];
+        const double c = g / nk + (a == b ? reg : 0.0);
+        Cm[i] = c;
+        if (b <= a) Ls[a * (a + 1) / 2 + b] = c;
+        else U[i] = 0.0;   // placeholder; the upper triangle is overwritten by Z^T below
     }
     __syncthreads();
-    for (int i = tid; i < D * D; i += T) Cm[i] = U[i];
-    __syncthreads();
-    // right-looking Cholesky in U's storage (lower triangle holds L)
+    // right-looking Cholesky, two barriers per column
     for (int j = 0; j < D; ++j) {
-        if (tid == 0) {
-            const double d = U[j * D + j];
-            if (!(d > 0)) s_bad = 1;
-            s_piv = sqrt(d);
-            U[j * D + j] = s_piv;
-        }
+        const int jj = j * (j + 1) / 2 + j;
+        const double d = Ls[jj];              // final since the barrier that closed column j - 1; the same value in every thread
+        if (!(d > 0)) { if (tid == 0) s_bad = 1; break; }
+        const double piv = sqrt(d);
+        for (int i = j + 1 + tid; i < D; i += T) { const double v = Ls[i * (i + 1) / 2 + j] / piv; Ls[i * (i + 1) / 2 + j] = v; s_col[i] = v; }
         __syncthreads();
-        if (s_bad) break;
-        const double piv = s_piv;
-        for (int i = j + 1 + tid; i < D; i += T) U[i * D + j] = U[i * D + j] / piv;
-        __syncthreads();
-        const int m = D - j - 1;
-        for (int idx = tid; idx < m * m; idx += T) {
-            const int i = j + 1 + idx / m, c = j + 1 + idx % m;
-            if (c <= i) U[i * D + c] = fma(-U[i * D + j], U[c * D + j], U[i * D + c]);
+        if (tid == 0) Ls[jj] = piv;           // nobody reads the diagonal of a finished column before the loop ends
+        // trailing update L[i][c] -= L[i][j] L[c][j]: a warp per row i, lanes over c <= i, column j from shared memory
+        for (int i = j + 1 + wid; i < D; i += nw) {
+            const int ri = i * (i + 1) / 2;
+            const double li = s_col[i];
+            for (int c = j + 1 + lane; c <= i; c += 32) Ls[ri + c] = fma(-li, s_col[c], Ls[ri + c]);
         }
         __syncthreads();
     }
+    __syncthreads();
     if (s_bad) {
         if (tid == 0) { w.state[init * 4 + 1] = 1.0; w.state[init * 4 + 3] = 1.0; } // done, failed
         return;
     }
-    // Z = L^-1 (lower) by forward substitution, one warp per column c:
+    // Z = L^-1 (lower) by forward substitution, one warp per column c, the column in registers (lane l holds Z[c + l + 32 q][c]):
     //     Z[c][c] = 1 / L[c][c],   Z[r][c] = -(sum_{p=c}^{r-1} L[r][p] Z[p][c]) / L[r][r]   (r > c)
-    // Z[p][c] is written to the UPPER triangle at U[c][p] -- that is prec_chol = Z^T, exactly where it has to end up; the strict
-    // lower triangle keeps L until every column is done, the diagonal of L moves to shared memory first.
-    __shared__ double s_diag[DBIG];
-    for (int j = tid; j < D; j += T) s_diag[j] = U[j * D + j];
-    __syncthreads();
-    const int lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+    // prec_chol = Z^T: column c of Z is row c of U.
+    constexpr int ZQ = (DBIG + 31) / 32;
     for (int c = wid; c < D; c += nw) {
-        if (lane == 0) U[c * D + c] = 1.0 / s_diag[c];
-        __syncwarp();
+        double z[ZQ];
+#pragma unroll
+        for (int q = 0; q < ZQ; ++q) z[q] = 0.0;
+        if (lane == 0) z[0] = 1.0 / Ls[c * (c + 1) / 2 + c];
         for (int r = c + 1; r < D; ++r) {
+            const int rr = r * (r + 1) / 2;
             double sum = 0;
-            for (int p = c + lane; p < r; p += 32) sum = fma(U[r * D + p], U[c * D + p], sum);
+#pragma unroll
+            for (int q = 0; q < ZQ; ++q) {
+                const int pp = c + lane + 32 * q;
+                if (pp < r) sum = fma(Ls[rr + pp], z[q], sum);
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane == 0) U[c * D + r] = -sum / s_diag[r];
-            __syncwarp();
+            const double val = -sum / Ls[rr + r];
+            const int owner = (r - c) & 31, slot = (r - c) >> 5;
+#pragma unroll
+            for (int q = 0; q < ZQ; ++q) if (q == slot && lane == owner) z[q] = val;
+        }
+#pragma unroll
+        for (int q = 0; q < ZQ; ++q) {
+            const int pp = c + lane + 32 * q;
+            if (pp < D) U[(size_t)c * D + pp] = z[q];
         }
     }
-    __syncthreads();
+    // zero below the diagonal (the E-step multiplies by the whole matrix)
     for (int i = tid; i < D * D; i += T) { const int a = i / D, b = i % D; if (a > b) U[i] = 0.0; }
-    __syncthreads();
-    // log|prec_chol| + log weight, b = mu U, weight
-    if (tid == 0) {
+    // log|prec_chol| + log weight
+    if (wid == 0) {
         double ld = 0;
-        for (int j = 0; j < D; ++j) ld -= log(s_diag[j]);
-        w.ldw[init * K + k] = ld + log(nk / N);
+        for (int j = lane; j < D; j += 32) ld -= log(Ls[j * (j + 1) / 2 + j]);
+        s_ld[lane] = ld;
+        __syncwarp();
+        if (lane == 0) {
+            double t = 0;
+            for (int i = 0; i < 32; ++i) t += s_ld[i];
+            w.ldw[init * K + k] = t + log(nk / N);
+        }
     }
+    __syncthreads();   // U complete (global memory, visible to the whole CTA)
     for (int j = tid; j < D; j += T) {
         double a = 0;
-        for (int i = 0; i <= j; ++i) a = fma(mu[i], U[i * D + j], a);
+        for (int i = 0; i <= j; ++i) a = fma(mu[i], U[(size_t)i * D + j], a);
         w.bvec[((size_t)init * K + k) * D + j] = a;
     }
-    __syncthreads();
     if (tid == 0) wts[k] = nk / N;
 }
 
@@ -684,7 +813,11 @@ __global__ void __launch_bounds__(256) k_big_estep(int N_in, const int* n_dev, i
         for (int k = 0; k < K; ++k) s += exp(lw[k] - mx);
         lse = mx + log(s);
         if (lane == 0)
-            for (int k = 0; k < K; ++k) w.resp[((size_t)init * N_in + n) * K + k] = exp(lw[k] - lse);
+            for (int k = 0; k < K; ++k) {
+                const double r = exp(lw[k] - lse);
+                w.resp[((size_t)init * N_in + n) * K + k] = r;
+                w.sresp[((size_t)init * N_in + n) * K + k] = sqrt(r);
+            }
     }
     if (lane == 0) s_lse[wl] = lse;
     __syncthreads();
@@ -723,37 +856,85 @@ __global__ void k_big_converge(int N_in, const int* n_dev, int D, int K, int n_i
     if (threadIdx.x == 0) *w.flag = s_running;
 }
 
+// the restart with the largest lower bound among those that did not fail (-1: all failed) -> w.flag[0]
+__global__ void k_big_best(int D, int K, int n_init, GmmWs w)
+{
+    const int ps = pstride(K, D);
+    int best = -1;
+    double bl = 0;
+    for (int i = 0; i < n_init; ++i) {
+        const double* tail = w.par + (size_t)i * ps + K + K * D + 2 * (size_t)K * D * D;
+        if (tail[3] != 0.0 && (best < 0 || tail[0] > bl)) { best = i; bl = tail[0]; }
+    }
+    *w.flag = best;
+}
+
+// predict_proba of the best restart from Y = X U (in w.big, slots 0..K-1), and the exported parameters
+__global__ void __launch_bounds__(256) k_big_proba(int N_in, const int* n_dev, int D, int K, int best, GmmWs w, double* proba, double* params_out)
+{
+    const int N = n_dev ? min(*n_dev, N_in) : N_in;
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int n = blockIdx.x * 8 + wl;
+    if (n < N) {
+        double lw[KMAX];
+        double mx = -DBL_MAX;
+        for (int k = 0; k < K; ++k) {
+            const double* y = w.big + ((size_t)k * N_in + n) * D;
+            const double* b = w.bvec + ((size_t)best * K + k) * D;
+            double q = 0;
+            for (int j = lane; j < D; j += 32) { const double t = y[j] - b[j]; q = fma(t, t, q); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            lw[k] = -0.5 * (D * 1.8378770664093453 + q) + w.ldw[best * K + k];
+            mx = fmax(mx, lw[k]);
+        }
+        double s = 0;
+        for (int k = 0; k < K; ++k) s += exp(lw[k] - mx);
+        const double lse = mx + log(s);
+        if (lane == 0)
+            for (int k = 0; k < K; ++k) proba[(size_t)n * K + k] = exp(lw[k] - lse);
+    }
+    if (blockIdx.x == 0 && params_out) {
+        const int ps = pstride(K, D);
+        const double* par = w.par + (size_t)best * ps;
+        for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) params_out[i] = w.scale[i];
+        for (int i = threadIdx.x; i < ps; i += blockDim.x) params_out[2 * D + i] = par[i];
+        if (threadIdx.x == 0) params_out[2 * D + ps] = (double)best;
+    }
+}
+
 static int fit_big(int N, const int* n_dev, int D, int K, int n_init, int max_iter, double tol, double reg, unsigned long long seed,
-                   const int* init_labels, GmmWs& w, cudaStream_t st)
+                   const int* init_labels, GmmWs& w, cudaStream_t st, int* best_out)
 {
     ISB_REQUIRE(n_init <= 1024, "too many restarts");
     const int RK = n_init * K;
     const size_t sND = (size_t)N * D, sDD = (size_t)D * D;
     const int ps = pstride(K, D);
+    const size_t chol_smem = sizeof(double) * (size_t)D * (D + 1) / 2;
+    ISB_CUDA_CHECK(cudaFuncSetAttribute(k_big_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
     auto m_step = [&]() -> int {
-        k_big_means<<<dim3(K, n_init), 256, 0, st>>>(N, n_dev, D, K, w);
+        k_big_means<<<dim3(K, n_init, (D + 31) / 32), 1024, 0, st>>>(N, n_dev, D, K, w);
         ISB_LAUNCH_CHECK();
-        k_big_weighted<<<dim3((unsigned)((sND + 255) / 256), K, n_init), 256, 0, st>>>(N, n_dev, D, K, w);
-        ISB_LAUNCH_CHECK();
-        // Gram matrices straight into the covariance slots of the parameter blocks (par + r * ps + K + K D + k D D)
+        // split-K partial Gram matrices (tiles on or above the diagonal); k_big_chol adds them
         {
-            const BatchStride bs = { (size_t)K * sND, sND, (size_t)K * sND, sND, (size_t)ps, sDD };
-            k_dgemm_batched<true><<<dim3((D + TN - 1) / TN, (D + TM - 1) / TM, RK), 256, 0, st>>>(
-                w.big, D, w.big, D, w.par + K + K * D, D, bs, D, D, N, n_dev, 0, w.state, K);
+            const BatchStride bs = { 0, 0, 0, 0, (size_t)K * KS * sDD, (size_t)KS * sDD, sDD };
+            const FuseW fw = { w.sresp, w.par + K, (size_t)N * K, K, (size_t)ps, D };
+            k_dgemm_batched<true, true><<<dim3((D + TN - 1) / TN, (D + TM - 1) / TM, RK * KS), 256, 0, st>>>(
+                w.xs, D, w.xs, D, w.gram, D, bs, D, D, N, n_dev, 0, w.state, K, 1, KS, 0, fw);
             ISB_LAUNCH_CHECK();
         }
-        k_big_chol<<<dim3(K, n_init), 1024, 0, st>>>(N, n_dev, D, K, reg, w);
+        k_big_chol<<<dim3(K, n_init), 1024, chol_smem, st>>>(N, n_dev, D, K, reg, w);
         ISB_LAUNCH_CHECK();
         return ISB_OK;
     };
-    k_big_init<<<n_init, GT, 0, st>>>(N, n_dev, D, K, seed, init_labels, w);
+    k_big_init<<<n_init * CLI, GT, 0, st>>>(N, n_dev, D, K, seed, init_labels, w);
     ISB_LAUNCH_CHECK();
     if (int rc = m_step()) return rc;
     for (int it = 1; it <= max_iter; ++it) {
         {
-            const BatchStride bs = { 0, 0, (size_t)ps, sDD, (size_t)K * sND, sND };
-            k_dgemm_batched<false><<<dim3((D + TN - 1) / TN, (N + TM - 1) / TM, RK), 256, 0, st>>>(
-                w.xs, D, w.par + K + K * D + (size_t)K * sDD, D, w.big, D, bs, N, D, D, n_dev, 1, w.state, K);
+            const BatchStride bs = { 0, 0, (size_t)ps, sDD, (size_t)K * sND, sND, 0 };
+            k_dgemm_batched<false, false><<<dim3((D + TN - 1) / TN, (N + TM - 1) / TM, RK), 256, 0, st>>>(
+                w.xs, D, w.par + K + K * D + (size_t)K * sDD, D, w.big, D, bs, N, D, D, n_dev, 1, w.state, K, 0, 1, 1, FuseW());
             ISB_LAUNCH_CHECK();
         }
         k_big_estep<<<dim3((N + 7) / 8, n_init), 256, 0, st>>>(N, n_dev, D, K, w);
@@ -765,6 +946,17 @@ static int fit_big(int N, const int* n_dev, int D, int K, int n_init, int max_it
         ISB_CUDA_CHECK(cudaMemcpyAsync(&running, w.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         ISB_CUDA_CHECK(cudaStreamSynchronize(st));
         if (running == 0) break;
+    }
+    k_big_best<<<1, 1, 0, st>>>(D, K, n_init, w);
+    ISB_LAUNCH_CHECK();
+    ISB_CUDA_CHECK(cudaMemcpyAsync(best_out, w.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ISB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (*best_out >= 0) {
+        // Y = X U of the winner into the first K slots of the big buffer
+        const BatchStride bs = { 0, 0, 0, sDD, 0, sND, 0 };
+        k_dgemm_batched<false, false><<<dim3((D + TN - 1) / TN, (N + TM - 1) / TM, K), 256, 0, st>>>(
+            w.xs, D, w.par + (size_t)*best_out * ps + K + K * D + (size_t)K * sDD, D, w.big, D, bs, N, D, D, n_dev, 1, nullptr, K, 0, 1, 1, FuseW());
+        ISB_LAUNCH_CHECK();
     }
     return ISB_OK;
 }
@@ -821,7 +1013,10 @@ static size_t carve_gmm(GmmWs& w, void* ws, size_t bytes, int N, int D, int K, i
         w.bvec = c.take<double>((size_t)n_init * K * D);
         w.ldw = c.take<double>((size_t)n_init * K);
         w.lowpart = c.take<double>((size_t)n_init * ((N + 7) / 8));
-        w.cent = c.take<double>((size_t)n_init * K * D);
+        w.cent = c.take<double>((size_t)n_init * 2 * K * D);
+        w.iflag = c.take<int>((size_t)n_init * CLI);
+        w.gram = c.take<double>((size_t)n_init * K * KS * D * D);
+        w.sresp = c.take<double>((size_t)n_init * N * K);
         w.tot = c.take<double>((size_t)n_init * K * (1 + D));
         w.state = c.take<double>((size_t)n_init * 4);
         w.flag = c.take<int>(1);
@@ -851,11 +1046,20 @@ extern "C" int isb_gmm_fit_predict(const double* feat, int N, int D, int ld, con
     ISB_REQUIRE(need <= ws_bytes, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(ISB_PROF_GMM, st);
-    k_gmm_scale<<<1, GT, 0, st>>>(feat, N, n_dev, D, ld, use_scaler, w);
-    ISB_LAUNCH_CHECK();
     if (D > DMAX) {
-        if (int rc = fit_big(N, n_dev, D, K, n_init, max_iter, tol, reg_covar, seed, init_labels, w, st)) return rc;
+        int best = -1;
+        k_big_scale<<<(D + 31) / 32, 1024, 0, st>>>(feat, N, n_dev, D, ld, use_scaler, w);
+        ISB_LAUNCH_CHECK();
+        if (int rc = fit_big(N, n_dev, D, K, n_init, max_iter, tol, reg_covar, seed, init_labels, w, st, &best)) return rc;
+        if (best >= 0) {
+            k_big_proba<<<(N + 7) / 8, 256, 0, st>>>(N, n_dev, D, K, best, w, proba, params_out);
+            ISB_LAUNCH_CHECK();
+            return ISB_OK;
+        }
+        // every restart failed: fall through to k_gmm_predict, which reports it (NaN probabilities, ok = 0)
     } else {
+        k_gmm_scale<<<1, GT, 0, st>>>(feat, N, n_dev, D, ld, use_scaler, w);
+        ISB_LAUNCH_CHECK();
         k_gmm_fit<<<n_init, GT, 0, st>>>(N, n_dev, D, K, max_iter, tol, reg_covar, seed, init_labels, w);
         ISB_LAUNCH_CHECK();
     }
