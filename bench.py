@@ -273,7 +273,7 @@ def run_ours(args):
     lib.isb_profile_enable(0)
     ms_e2e, (segm, soft) = timed(step_e2e, args.steps)
     # extra (not the headline): a batch of images through the pipelined batch API -- upload / kernels / download of consecutive
-    # images overlap on two streams (what the reference's process pool over images becomes on a GPU)
+    # images overlap on three streams (what the reference's process pool over images becomes on a GPU)
     nbatch = 8
 
     def batch_once():
@@ -309,7 +309,7 @@ def run_ours(args):
         'e2e': {'value': e2e, 'unit': 'MPix/s', 'ms_per_step': ms_e2e / args.steps, 'h2d_bytes_per_step': int(host_np.nbytes),
                 'd2h_bytes_per_step': int(segm.nbytes + soft.nbytes)},
         'e2e_batch': {'value': world * 2 * nbatch * mpix / (ms_batch / 1e3), 'unit': 'MPix/s', 'images_per_call': nbatch,
-                      'note': 'segment_images_batch: same host-in/host-out path, copies of consecutive images overlapped on 2 streams'},
+                      'note': 'segment_images_batch: same host-in/host-out path, copies of consecutive images overlapped on 3 streams'},
         'gpu_launches': int(launches),
         'roofline': {'kernel': 'k_assign (slic_assign)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': achieved / peak, 'traffic': load_traffic(), 'traffic_source': 'profiles/r01d_ncu_top_kernels.md', 'peak_source': peak_src,

@@ -212,7 +212,7 @@ def _batch_engines(nb_streams):
 
 
 def segment_images_batch(list_images, nb_classes=None, dict_features=FTS_SET_SIMPLE, sp_size=30, sp_regul=0.2, use_scaler=True,
-                         gc_regul=1., gc_edge_type='model', model_pipeline=None, nb_streams=2, max_in_flight=4):
+                         gc_regul=1., gc_edge_type='model', model_pipeline=None, nb_streams=3, max_in_flight=6):
     """ the hot path over a LIST of images, the way the reference's experiment scripts run it through a process pool
     (``run_segm_slic_model_graphcut.py:461-466``): here consecutive images alternate over ``nb_streams`` CUDA streams with
     their own buffers, so the upload of image i+1 and the download of image i-1 overlap the kernels of image i.
