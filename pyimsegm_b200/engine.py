@@ -100,6 +100,12 @@ class Engine(object):
             self.torch.cuda.current_stream().synchronize()
         return out.numpy()
 
+    def side_stream(self):
+        """a second CUDA stream of this engine (copies that may overlap the kernels of the main stream)"""
+        if getattr(self, '_side', None) is None:
+            self._side = self.torch.cuda.Stream(device=self.device)
+        return self._side
+
     def _ck(self, rc):
         _lib.check(rc)
 

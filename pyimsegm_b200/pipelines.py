@@ -118,10 +118,12 @@ def _argmin_labels_device(eng, proba):
 EDGE_CAP_PER_NODE = [8]
 
 
-def _run_resident(eng, image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type):
+def _run_resident(eng, image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type, soft_sink=None):
     """the whole hot path on the device.  ``model`` is either ('fit', nb_classes, use_scaler, max_iter) -> the default
     GMM is fitted on the GPU and NOTHING syncs with the host until the results are ready; or a callable
     proba_fn(features) -> one round trip (features down, probabilities up) as in the reference.
+    ``soft_sink(d_seg, d_proba)``: the caller takes ``segm_soft = proba[slic]`` itself as soon as the probabilities exist
+    (it does not depend on the graph cut) -- then ``d_soft`` is returned as None.
     Returns (d_segm, d_soft, check): ``check`` is None or (d_n_edges, edge_cap) still to be verified by the caller."""
     res = _device_slic_features(eng, image, dict_features, sp_size, sp_regul)
     no_cut = (not isinstance(gc_regul, (list, np.ndarray))) and gc_regul <= 0
@@ -136,8 +138,10 @@ def _run_resident(eng, image, model, dict_features, sp_size, sp_regul, gc_regul,
             d_labels = _argmin_labels_device(eng, eng.to_host(d_proba[:nb]))
             return eng.gather(res.d_seg, d_labels, d_proba) + (None, )
         cap = max(64, EDGE_CAP_PER_NODE[0] * res.nb_bound)
+        if soft_sink is not None:
+            soft_sink(res.d_seg, d_proba)
         _, d_segm, d_soft, d_n_edges, cap = _device_graphcut(eng, res, res.nb_bound, d_proba, nb_classes, gc_regul, gc_edge_type,
-                                                             d_n_nodes=res.d_n_labels, edge_cap=cap)
+                                                             d_n_nodes=res.d_n_labels, want_soft=soft_sink is None, edge_cap=cap)
         return d_segm, d_soft, (d_n_edges, cap)
     nb = int(eng.to_host(res.d_n_labels)[0])
     features = eng.to_host(res.d_feat[:nb]).copy()
@@ -148,7 +152,10 @@ def _run_resident(eng, image, model, dict_features, sp_size, sp_regul, gc_regul,
     if no_cut:
         return eng.gather(res.d_seg, _argmin_labels_device(eng, proba), d_proba) + (None, )
     cap = max(64, EDGE_CAP_PER_NODE[0] * nb)
-    _, d_segm, d_soft, d_n_edges, cap = _device_graphcut(eng, res, nb, d_proba, proba.shape[1], gc_regul, gc_edge_type, edge_cap=cap)
+    if soft_sink is not None:
+        soft_sink(res.d_seg, d_proba)
+    _, d_segm, d_soft, d_n_edges, cap = _device_graphcut(eng, res, nb, d_proba, proba.shape[1], gc_regul, gc_edge_type,
+                                                         want_soft=soft_sink is None, edge_cap=cap)
     return d_segm, d_soft, (d_n_edges, cap)
 
 
@@ -183,12 +190,33 @@ def _segment(image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_t
         if classes is not None:
             graph_labels = classes[graph_labels]
         return graph_labels[slic], segm_soft
+    torch = eng.torch
+    early = {}
+
+    def soft_sink(d_seg, d_proba):
+        # segm_soft = proba[slic] needs only the class probabilities: its gather and its (large) download run on a side stream
+        # while the main stream builds and cuts the graph
+        side = eng.side_stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            _, d_soft = eng.gather(d_seg, None, d_proba)
+            host = eng.pinned_empty(d_soft.shape, d_soft.dtype)
+            host.copy_(d_soft, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record(side)
+        early['host'], early['event'] = host, event
+
     while True:
-        d_segm, d_soft, check = _run_resident(eng, image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)
-        if check is None:
+        early.clear()
+        d_segm, d_soft, check = _run_resident(eng, image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type,
+                                              soft_sink=soft_sink)
+        if check is None:   # no graph cut: both gathers were done at the end of the main stream
             segm, soft = _download_results(eng, (d_segm, d_soft))
             break
-        segm, soft, n_edges = _download_results(eng, (d_segm, d_soft, check[0]))
+        segm, n_edges = _download_results(eng, (d_segm, check[0]))
+        early['event'].synchronize()
+        soft = early['host'].numpy()
+        # the next call reuses the buffers the side stream has just read: nothing of this call is left in flight
         if int(n_edges[0]) <= check[1]:
             break
         EDGE_CAP_PER_NODE[0] *= 4  # the device edge table overflowed (> 8 edges per superpixel on average): redo larger

@@ -15,3 +15,16 @@ n = 600; a = rng.randint(0, n, 2000); b = rng.randint(0, n, 2000); k = a != b
 e = np.unique(np.stack([np.minimum(a, b)[k], np.maximum(a, b)[k]], 1), axis=0).astype(np.int32)
 lab = gc.cut_general_graph(e, rng.rand(len(e)) + 0.01, gc.compute_unary_cost(rng.dirichlet(np.ones(4) * 2, n)), gc.compute_pairwise_cost(1.5, (n, 4)))
 print('gc ok', np.bincount(lab))
+# row-band mode (three bands in one process) and the large-D class model
+from pyimsegm_b200 import tiled
+from pyimsegm_b200.superpixels import slic_params
+n_seg, compact = slic_params(img.shape[:2], 12, 0.3)
+res = tiled.slic_tiled(img, n_seg, compact, bands_per_rank=3)
+print('banded slic ok', res.fell_back)
+res = tiled.slic_tiled(img, n_seg, compact, bands_per_rank=2, slic_zero=True)
+print('banded slico ok', res.fell_back)
+s2, p2, rows = tiled.pipe_color2d_slic_features_model_graphcut_tiled(img, 3, {'color': ['mean', 'std']}, sp_size=12, sp_regul=0.3, bands_per_rank=2)
+print('banded pipe ok', s2.shape, rows, bool(np.array_equal(s2, pl.pipe_color2d_slic_features_model_graphcut(img, 3, {'color': ['mean', 'std']}, sp_size=12, sp_regul=0.3)[0])))
+X = np.concatenate([c + rng.normal(0, 0.5, (120, 24)) for c in rng.normal(0, 2.0, (3, 24))])
+m = gc.estim_class_model(X, 3)
+print('large-D gmm ok', np.bincount(m.predict_proba(X).argmax(1)))
