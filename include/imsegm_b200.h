@@ -156,6 +156,31 @@ int isb_label_hist_2d(const int16_t* segm_select, const int16_t* struc_elem, int
 int isb_region_label_hist(const int32_t* slic, const int32_t* annot, int H, int W, int nb_slic, int nb_annot, uint32_t* hist,
                           isb_stream_t stream);
 
+/* compute_img_filter_response2d / 3d (imsegm/descriptors.py:951-983): per slice of img [n_slices, H, W] f64 the maximum over a
+ * battery of kernels [n_kernels, kh, kw] f64 (odd sizes) of scipy.ndimage.convolve(slice, kernel) -- true convolution, mode
+ * 'reflect'.  Generic FP64 utility for the gray-volume texture path; colour images use isb_lm_texture. */
+int isb_filter_response_2d(const double* img, int n_slices, int H, int W, const double* kernels, int n_kernels, int kh, int kw,
+                           double* out, isb_stream_t stream);
+
+/* scipy.ndimage.gaussian_filter of every slice of img [n_slices, H, W] f64 (rows, then columns; symmetric 1-D correlate, mode
+ * 'reflect'), what image_subtract_gauss_smooth (:986-1000) subtracts.  w_half: DEVICE, radius + 1 weights, [0] = centre;
+ * tmp: scratch of the image's size */
+int isb_gaussian_filter_2d(const double* img, int n_slices, int H, int W, const double* w_half, int radius, double* tmp, double* out,
+                           isb_stream_t stream);
+
+/* compute_label_histograms_positions (imsegm/descriptors.py:1288-1352) in one launch: for every position (row, col) and every
+ * diameter d the histogram of the labels under the disc dy^2 + dx^2 <= d^2 (skimage.morphology.disk(d)) clipped to the image,
+ * i.e. what compute_label_hist_segm (:1396) returns for the pair, and the pixel count of the clipped disc.
+ *   segm  : [H, W] i32 labels, values outside [0, nb_labels) ignored;  or proba [H, W, nb_labels] f64 (then segm may be NULL):
+ *           hist[l] = sum of proba[.., l] under the disc (compute_label_hist_proba :1501)
+ *   positions [n_pos, 2] i32 (row, col), diameters [n_diam] i32;  hist out [n_pos, n_diam, nb_labels] f64, sizes out [n_pos, n_diam] f64
+ *   selem : optional explicit structuring element [mh, mw] u8 (1 = inside) used instead of the discs (then n_diam must be 1,
+ *           diameters may be NULL); mask pixel (iy, ix) lies on image pixel (row - mh/2 + iy, col - mw/2 + ix) as in
+ *           adjust_bounding_box_crop (:1355) */
+int isb_disc_label_hist(const int32_t* segm, const double* proba, int H, int W, const int32_t* positions, int n_pos,
+                        const int32_t* diameters, int n_diam, const uint8_t* selem, int mh, int mw, int nb_labels, double* hist,
+                        double* sizes, isb_stream_t stream);
+
 /* computeRayFeaturesBinary2d (features_cython.pyx:239) for n_pos positions at once: out [n_pos, n_ang] f32, -1 where the ray
  * leaves the image, 0 where the position lies inside the border label (edge 'up').  sin_a / cos_a: the f32 sines and cosines
  * of the ray angles as the reference forms them (np.deg2rad of the f32 angle, stored to float).  edge: 1 'up', -1 'down'. */

@@ -423,3 +423,56 @@ def ray_features2d(seg_binary, position, angle_step=5., edge=1):
     lib().oracle_ray_features2d(_p(seg, C.c_int8), seg.shape[0], seg.shape[1], int(position[0]), int(position[1]),
                                 _p(s, C.c_float), _p(c, C.c_float), len(s), int(edge), _p(out, C.c_float))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# label histograms about positions (imsegm/descriptors.py:1288-1528) -- numpy restatement, pinned by the reference's doctests
+# ---------------------------------------------------------------------------------------------------------------------
+
+def disk(radius):
+    """skimage.morphology.disk: 1 where dy^2 + dx^2 <= radius^2 on a (2 r + 1)^2 grid"""
+    r = int(radius)
+    yy, xx = np.mgrid[-r:r + 1, -r:r + 1]
+    return (yy ** 2 + xx ** 2 <= r ** 2).astype(np.uint8)
+
+
+def label_hist_selem(segm, position, struc_elem, nb_labels=None):
+    """compute_label_hist_segm (:1396) / compute_label_hist_proba (:1501): the element is centred on the position with
+    adjust_bounding_box_crop's rule (:1355): element pixel (iy, ix) lies on image pixel (row - mh // 2 + iy, col - mw // 2 + ix);
+    what falls outside the image is dropped.  Returns (hist, size)."""
+    segm, struc_elem = np.asarray(segm), np.asarray(struc_elem)
+    py, px = int(position[0]), int(position[1])
+    mh, mw = struc_elem.shape
+    H, W = segm.shape[:2]
+    nb = (int(nb_labels) if nb_labels is not None else int(segm.max()) + 1) if segm.ndim == 2 else segm.shape[-1]
+    hist = np.zeros(nb)
+    size = 0
+    for iy in range(mh):
+        for ix in range(mw):
+            y, x = py - mh // 2 + iy, px - mw // 2 + ix
+            if struc_elem[iy, ix] != 1 or y < 0 or y >= H or x < 0 or x >= W:
+                continue
+            size += 1
+            if segm.ndim == 2:
+                if 0 <= segm[y, x] < nb:
+                    hist[int(segm[y, x])] += 1
+            else:
+                hist += segm[y, x]
+    return hist, size
+
+
+def label_histograms_positions(segm, positions, diameters, nb_labels=None):
+    """compute_label_histograms_positions (:1288-1352): per position, per ring (disc d_i minus disc d_{i-1}) the label
+    histogram divided by the ring's pixel count"""
+    segm = np.asarray(segm)
+    if nb_labels is None:
+        nb_labels = int(segm.max()) + 1 if segm.ndim == 2 else segm.shape[-1]
+    rows = []
+    for pos in positions:
+        last_h, last_s, row = np.zeros(nb_labels), 0, []
+        for d in diameters:
+            h, sz = label_hist_selem(segm, pos, disk(d), nb_labels)
+            row += ((h - last_h) / float(sz - last_s)).tolist()
+            last_h, last_s = h, sz
+        rows.append(row)
+    return np.array(rows)

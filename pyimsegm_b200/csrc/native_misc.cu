@@ -189,3 +189,150 @@ extern "C" int isb_ray_features_2d(const int8_t* seg_binary, int H, int W, const
     ISB_LAUNCH_CHECK();
     return ISB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// compute_label_histograms_positions (imsegm/descriptors.py:1288-1352): label histograms under discs of growing diameter
+// about a list of positions.  The reference crops the segmentation and a skimage.morphology.disk(d) mask per (position,
+// diameter) and calls computeLabelHistogram2d on the crop; here ONE launch covers every (position, diameter): a CTA per pair
+// walks the disc {(dy, dx): dy^2 + dx^2 <= d^2} clipped to the image (= adjust_bounding_box_crop, descriptors.py:1355-1393).
+//   segm   : [H, W] int32 labels (entries outside [0, nb_labels) are ignored), or -- when proba != nullptr -- unused
+//   proba  : optional [H, W, nb_labels] f64 (compute_label_hist_proba :1501-1528): hist[l] = sum of proba[..., l] under the disc
+//   hist   : out [n_pos, n_diam, nb_labels] f64;  sizes: out [n_pos, n_diam] f64 = pixels of the (clipped) disc
+//   selem  : optional explicit structuring element [mh, mw] u8 instead of the discs (then n_diam == 1): compute_label_hist_segm /
+//            compute_label_hist_proba with any mask; mask pixel (iy, ix) sits on image pixel (row - mh/2 + iy, col - mw/2 + ix)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) k_disc_hist(const int* __restrict__ segm, const double* __restrict__ proba, int H, int W,
+                                                   const int* __restrict__ positions, const int* __restrict__ diameters, int n_diam,
+                                                   const unsigned char* __restrict__ selem, int mh, int mw, int nb_labels,
+                                                   double* __restrict__ hist, double* __restrict__ sizes)
+{
+    extern __shared__ double s_hist[];   // [nb_labels] + 1 (size)
+    const int ip = blockIdx.x / n_diam, id = blockIdx.x % n_diam;
+    const int py = positions[2 * ip], px = positions[2 * ip + 1], d = selem ? 0 : diameters[id];
+    for (int i = threadIdx.x; i <= nb_labels; i += blockDim.x) s_hist[i] = 0.0;
+    __syncthreads();
+    const int sh = selem ? mh : 2 * d + 1, sw = selem ? mw : 2 * d + 1;
+    const int oy = selem ? mh / 2 : d, ox = selem ? mw / 2 : d;
+    double cnt = 0;
+    for (int i = threadIdx.x; i < sh * sw; i += blockDim.x) {
+        const int dy = i / sw - oy, dx = i % sw - ox;
+        if (selem ? selem[i] != 1 : dy * dy + dx * dx > d * d) continue;
+        const int y = py + dy, x = px + dx;
+        if (y < 0 || y >= H || x < 0 || x >= W) continue;
+        cnt += 1.0;
+        if (proba) {
+            const double* p = proba + ((size_t)y * W + x) * nb_labels;
+            for (int l = 0; l < nb_labels; ++l) atomicAdd(&s_hist[l], p[l]);
+        } else {
+            const int l = segm[(size_t)y * W + x];
+            if (l >= 0 && l < nb_labels) atomicAdd(&s_hist[l], 1.0);
+        }
+    }
+    atomicAdd(&s_hist[nb_labels], cnt);
+    __syncthreads();
+    double* out = hist + ((size_t)ip * n_diam + id) * nb_labels;
+    for (int i = threadIdx.x; i < nb_labels; i += blockDim.x) out[i] = s_hist[i];
+    if (threadIdx.x == 0) sizes[(size_t)ip * n_diam + id] = s_hist[nb_labels];
+}
+
+} // namespace
+
+extern "C" int isb_disc_label_hist(const int32_t* segm, const double* proba, int H, int W, const int32_t* positions, int n_pos,
+                                   const int32_t* diameters, int n_diam, const uint8_t* selem, int mh, int mw, int nb_labels,
+                                   double* hist, double* sizes, isb_stream_t stream)
+{
+    ISB_REQUIRE((segm || proba) && positions && (diameters || selem) && hist && sizes, "null pointer");
+    ISB_REQUIRE(H > 0 && W > 0 && n_pos > 0 && n_diam > 0 && nb_labels > 0 && nb_labels <= 4096, "bad sizes");
+    ISB_REQUIRE(!selem || (n_diam == 1 && mh > 0 && mw > 0), "an explicit structuring element replaces the list of diameters");
+    k_disc_hist<<<n_pos * n_diam, 256, sizeof(double) * (nb_labels + 1), (cudaStream_t)stream>>>(segm, proba, H, W, positions, diameters, n_diam,
+                                                                                           selem, mh, mw, nb_labels, hist, sizes);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Generic (any image, any odd kernels) FP64 versions of two host helpers of imsegm/descriptors.py that the gray-volume
+// texture path is built from -- the colour path has its own fused tensor-core kernel (lm_texture.cu):
+//   compute_img_filter_response2d :951-966  : max over a battery of ndimage.convolve(img, kernel) (true convolution, 'reflect')
+//   image_subtract_gauss_smooth   :986-1000 : per-slice scipy gaussian_filter (rows then columns, symmetric 1-D correlate, 'reflect')
+// Plain direct sums in IEEE double in scipy's order; these are utilities, not hot-path kernels.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ int reflect_at(int i, int n)
+{
+    if (n == 1) return 0;
+    const int p = 2 * n;
+    i %= p;
+    if (i < 0) i += p;
+    return i < n ? i : p - 1 - i;
+}
+
+// out[s][y][x] = max_f sum_{a,b} K[f][a][b] img[s][reflect(y + kh/2 - a)][reflect(x + kw/2 - b)]
+__global__ void __launch_bounds__(256) k_conv_battery_max(const double* __restrict__ img, int S, int H, int W, const double* __restrict__ kern,
+                                                          int nf, int kh, int kw, double* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)S * H * W) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const double* im = img + (i / ((size_t)H * W)) * (size_t)H * W;
+    double best = 0.0;
+    for (int f = 0; f < nf; ++f) {
+        const double* k = kern + (size_t)f * kh * kw;
+        double acc = 0.0;
+        // ndimage.convolve == correlate with the flipped kernel: walk the flipped kernel in C order
+        for (int a = kh - 1; a >= 0; --a) {
+            const int yy = reflect_at(y + kh / 2 - a, H);
+            for (int b = kw - 1; b >= 0; --b) acc = __dadd_rn(acc, __dmul_rn(k[a * kw + b], im[(size_t)yy * W + reflect_at(x + kw / 2 - b, W)]));
+        }
+        best = (f == 0 || acc > best) ? acc : best;   // np.max over the battery (NaN handling is not needed: inputs are finite)
+    }
+    out[i] = best;
+}
+
+// one axis of scipy's gaussian_filter on [S, H, W]: axis 0 = rows (y), 1 = columns (x)
+__global__ void __launch_bounds__(256) k_gauss_axis(const double* __restrict__ in, int S, int H, int W, int axis, const double* __restrict__ w_half,
+                                                    int r, double* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)S * H * W) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const double* im = in + (i / ((size_t)H * W)) * (size_t)H * W;
+    double t = __dmul_rn(im[(size_t)y * W + x], w_half[0]);
+    for (int j = r; j >= 1; --j) {
+        double a, b;
+        if (axis == 0) { a = im[(size_t)reflect_at(y - j, H) * W + x]; b = im[(size_t)reflect_at(y + j, H) * W + x]; }
+        else { a = im[(size_t)y * W + reflect_at(x - j, W)]; b = im[(size_t)y * W + reflect_at(x + j, W)]; }
+        t = __dadd_rn(t, __dmul_rn(__dadd_rn(a, b), w_half[j]));
+    }
+    out[i] = t;
+}
+
+} // namespace
+
+extern "C" int isb_filter_response_2d(const double* img, int n_slices, int H, int W, const double* kernels, int n_kernels, int kh, int kw,
+                                      double* out, isb_stream_t stream)
+{
+    ISB_REQUIRE(img && kernels && out, "null pointer");
+    ISB_REQUIRE(n_slices > 0 && H > 0 && W > 0 && n_kernels > 0 && kh > 0 && kw > 0, "bad sizes");
+    ISB_REQUIRE((kh & 1) && (kw & 1), "kernels must have odd sizes");
+    const size_t n = (size_t)n_slices * H * W;
+    k_conv_battery_max<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img, n_slices, H, W, kernels, n_kernels, kh, kw, out);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
+extern "C" int isb_gaussian_filter_2d(const double* img, int n_slices, int H, int W, const double* w_half, int radius, double* tmp, double* out,
+                                      isb_stream_t stream)
+{
+    ISB_REQUIRE(img && w_half && tmp && out, "null pointer");
+    ISB_REQUIRE(n_slices > 0 && H > 0 && W > 0 && radius >= 0, "bad sizes");
+    const size_t n = (size_t)n_slices * H * W;
+    k_gauss_axis<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img, n_slices, H, W, 0, w_half, radius, tmp);
+    ISB_LAUNCH_CHECK();
+    k_gauss_axis<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(tmp, n_slices, H, W, 1, w_half, radius, out);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}

@@ -239,6 +239,502 @@ def cython_ray_features_seg2d(seg_binary, position, angle_step=5., edge='up'):
     return res[0] if np.ndim(position) == 1 else res
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# gray volumes: host (NumPy) variants and the statistic driver (reference descriptors.py:545-787)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _gray_counts(seg):
+    nb = int(np.max(seg)) + 1
+    cnt = np.bincount(np.ravel(seg), minlength=nb).astype(float)
+    cnt[cnt == 0] = -1          # "just for not dividing by 0"
+    return nb, cnt
+
+
+def numpy_img3d_gray_mean(img, seg):
+    """ f64 host computation of the mean intensity per segment of a gray volume (reference descriptors.py:545-580) """
+    img, seg = np.asarray(img, dtype=float), np.asarray(seg)
+    _check_gray_image_segm(img, seg)
+    nb, cnt = _gray_counts(seg)
+    return np.bincount(seg.ravel(), weights=img.ravel(), minlength=nb) / cnt
+
+
+def numpy_img3d_gray_std(img, seg, means=None):
+    """ f64 host computation of the intensity STD per segment of a gray volume (reference descriptors.py:583-617) """
+    img, seg = np.asarray(img, dtype=float), np.asarray(seg)
+    _check_gray_image_segm(img, seg)
+    if means is None:
+        means = numpy_img3d_gray_mean(img, seg)
+    nb, cnt = _gray_counts(seg)
+    if len(means) < nb:
+        raise ValueError('number of means (%i) should be equal to number of labels (%i)' % (len(means), nb))
+    var = np.bincount(seg.ravel(), weights=((img - np.asarray(means)[seg]) ** 2).ravel(), minlength=nb) / cnt
+    var[var == 0] = 0
+    return np.sqrt(var)
+
+
+def numpy_img3d_gray_energy(img, seg):
+    """ f64 host computation of the mean squared intensity per segment of a gray volume (reference descriptors.py:620-648) """
+    img, seg = np.asarray(img, dtype=float), np.asarray(seg)
+    _check_gray_image_segm(img, seg)
+    nb, cnt = _gray_counts(seg)
+    return np.bincount(seg.ravel(), weights=(img ** 2).ravel(), minlength=nb) / cnt
+
+
+def numpy_img3d_gray_median(img, seg):
+    """ median intensity per segment of a gray volume (reference descriptors.py:651-676; NaN for absent labels) """
+    img, seg = np.asarray(img), np.asarray(seg)
+    _check_gray_image_segm(img, seg)
+    nb = int(seg.max()) + 1
+    flat = seg.ravel()
+    order = np.argsort(flat, kind='stable')
+    bounds = np.searchsorted(flat[order], np.arange(nb + 1))
+    vals = img.ravel()[order]
+    medians = np.full(nb, np.nan)
+    for lb in range(nb):
+        if bounds[lb + 1] > bounds[lb]:
+            medians[lb] = np.median(vals[bounds[lb]:bounds[lb + 1]])
+    return medians
+
+
+def compute_image3d_gray_statistic(image, segm, feature_flags=NAMES_FEATURE_FLAGS, ch_name='gray'):
+    """ statistics of a gray volume over the segments (reference descriptors.py:679-784); mean / std / energy run in
+    ``isb_gray_stats`` (or the NumPy variants when ``USE_CYTHON`` is off, as in the reference)
+
+    :return tuple(ndarray,list(str)): features [nb_segments, nb_statistics], column names
+    """
+    image, segm = np.asarray(image), np.asarray(segm)
+    _check_gray_image_segm(image, segm)
+    if not list(feature_flags):
+        raise ValueError('some features has to be selected')
+    image = np.nan_to_num(image)
+    fn_mean = cython_img3d_gray_mean if USE_CYTHON else numpy_img3d_gray_mean
+    columns = {}
+    native = [f for f in ('mean', 'std', 'energy') if f in feature_flags]
+    if native and USE_CYTHON:
+        stats = _device_gray_stats(image, segm, native)       # one launch family for all three
+        for i, f in enumerate(native):
+            columns[f] = stats[:, i]
+    elif native:
+        mean = numpy_img3d_gray_mean(image, segm) if 'mean' in native else None
+        if 'mean' in native:
+            columns['mean'] = mean
+        if 'std' in native:
+            columns['std'] = numpy_img3d_gray_std(image, segm, mean)
+        if 'energy' in native:
+            columns['energy'] = numpy_img3d_gray_energy(image, segm)
+    if 'median' in feature_flags:
+        columns['median'] = numpy_img3d_gray_median(image, segm)
+    if 'meanGrad' in feature_flags:
+        grad = np.zeros(image.shape, dtype=image.dtype if image.dtype.kind == 'f' else float)
+        for i in range(image.shape[0]):
+            grad[i] = np.sum(np.gradient(image[i]), axis=0)
+        columns['meanGrad'] = fn_mean(grad, segm)
+    order = [f for f in NAMES_FEATURE_FLAGS if f in feature_flags]
+    names = ['%s_%s' % (ch_name, f) for f in order]
+    _check_unrecognised_feature_names(feature_flags)
+    nb = int(segm.max()) + 1
+    features = np.stack([columns[f] for f in order], axis=1) if order else np.empty((nb, 0))
+    features = np.nan_to_num(features)
+    features[features == 0] = 0
+    if features.shape[1] != len(names):
+        raise ValueError('features: %r and names %r' % (features.shape, names))
+    return features, names
+
+
+def _as_slices(img):
+    img = np.ascontiguousarray(img, dtype=np.float64)
+    if img.ndim not in (2, 3):
+        raise ValueError('expected a 2-D image or a stack of 2-D slices, got shape %r' % (img.shape, ))
+    return img, (img[np.newaxis] if img.ndim == 2 else img)
+
+
+def compute_img_filter_response2d(img, filter_battery):
+    """ the strongest response of a 2-D image over a battery of filters, ``max_f convolve(img, filter_f)`` (true convolution,
+    mode 'reflect'; reference descriptors.py:951-966) -- FP64 on the device (``isb_filter_response_2d``) """
+    filter_battery = np.ascontiguousarray(filter_battery, dtype=np.float64)
+    if filter_battery.ndim != 3:
+        raise ValueError('wrong battery dim %r' % (filter_battery.shape, ))
+    if np.ndim(img) != 2:
+        raise ValueError('expected a 2-D image, got shape %r' % (np.shape(img), ))
+    return compute_img_filter_response3d(np.asarray(img)[np.newaxis], filter_battery)[0]
+
+
+def compute_img_filter_response3d(img, filter_battery):
+    """ :func:`compute_img_filter_response2d` of every slice ``img[i]`` in one launch (reference descriptors.py:969-983) """
+    from . import _lib
+    filter_battery = np.ascontiguousarray(filter_battery, dtype=np.float64)
+    if filter_battery.ndim != 3:
+        raise ValueError('wrong battery dim %r' % (filter_battery.shape, ))
+    img = np.ascontiguousarray(img, dtype=np.float64)
+    if img.ndim != 3:
+        raise ValueError('expected a stack of 2-D slices, got shape %r' % (img.shape, ))
+    eng = get_engine()
+    d_img = eng.to_device(img, 'resp_img')
+    d_ker = eng.to_device(filter_battery, 'resp_kernels')
+    out = eng.buf('resp_out', img.shape, eng.torch.float64)
+    _lib.check(eng.lib.isb_filter_response_2d(_lib.ptr(d_img), img.shape[0], img.shape[1], img.shape[2], _lib.ptr(d_ker), filter_battery.shape[0],
+                                              filter_battery.shape[1], filter_battery.shape[2], _lib.ptr(out), _lib.stream_ptr()))
+    return eng.to_host(out).copy()
+
+
+def image_subtract_gauss_smooth(img, sigma):
+    """ subtract from every slice ``img[i]`` its own Gaussian-smoothed copy -- a high-pass per slice (reference
+    descriptors.py:986-1000; scipy's ``gaussian_filter`` semantics, FP64 on the device) """
+    from . import _lib
+    from .engine import gaussian_half_kernel
+    if sigma <= 0:
+        return img
+    src, stack = _as_slices(img)
+    if src.ndim != 3:
+        raise ValueError('expected a stack of 2-D slices, got shape %r' % (src.shape, ))
+    w_half, radius = gaussian_half_kernel(sigma)
+    eng = get_engine()
+    d_img = eng.to_device(stack, 'smooth_img')
+    d_w = eng.to_device(w_half, 'smooth_w')
+    tmp = eng.buf('smooth_tmp', stack.shape, eng.torch.float64)
+    out = eng.buf('smooth_out', stack.shape, eng.torch.float64)
+    _lib.check(eng.lib.isb_gaussian_filter_2d(_lib.ptr(d_img), stack.shape[0], stack.shape[1], stack.shape[2], _lib.ptr(d_w), radius,
+                                              _lib.ptr(tmp), _lib.ptr(out), _lib.stream_ptr()))
+    return np.asarray(img) - eng.to_host(out).reshape(src.shape)
+
+
+def compute_texture_desc_lm_img3d_val(img, seg, feature_flags, bank_type='normal'):
+    """ Leung-Malik texture statistics of a gray VOLUME (reference descriptors.py:1003-1038): slice-wise high-pass (sigma 150),
+    slice-wise battery responses, clipping, log-norm scaling over the whole volume, statistics over the 3-D segments.
+    Generic FP64 kernels (``isb_gaussian_filter_2d``, ``isb_filter_response_2d``, ``isb_gray_stats``): this is the completeness
+    path for volumes -- the tensor-core kernel of the hot path is :func:`compute_texture_desc_lm_img2d_clr`.
+
+    :return tuple(ndarray,list(str)): features [nb_segments, nb_batteries * nb_statistics], names
+    """
+    img, seg = np.asarray(img), np.asarray(seg)
+    _check_gray_image_segm(img, seg)
+    img = image_subtract_gauss_smooth(img, 150)
+    if bank_type == 'short':
+        filters, fl_names = create_filter_bank_lm_2d(sigmas=SHORT_FILTERS_SIGMAS, nb_orient=4)
+    else:
+        filters, fl_names = create_filter_bank_lm_2d()
+    features, names = [], []
+    for battery, fl_name in zip(filters, fl_names):
+        response = compute_img_filter_response3d(img, battery)
+        response[response > MAX_SIGNAL_RESPONSE] = MAX_SIGNAL_RESPONSE
+        l_n = np.sqrt(np.sum(np.power(response, 2)))
+        if l_n == 0 or abs(l_n) == np.inf:
+            response = np.zeros(response.shape)
+        else:
+            response = (response * (np.log(1 + l_n) / 0.03)) / l_n
+        fts, ns = compute_image3d_gray_statistic(response, seg, feature_flags, fl_name)
+        features.append(fts)
+        names += ns
+    features = np.nan_to_num(np.concatenate(tuple(features), axis=1))
+    features[features == 0] = 0
+    names = ['tLM_%s' % name for name in names]
+    if features.shape[1] != len(names):
+        raise ValueError('features: %r and names %r' % (features.shape, names))
+    return features, names
+
+
+def compute_selected_features_gray3d(img, segments, feature_flags=FEATURES_SET_COLOR):
+    """ selected features of a gray volume (reference descriptors.py:1109-1164): ``{'color': flags}`` -> intensity statistics,
+    ``{'tLM[_short]': flags}`` -> texture statistics (see :func:`compute_texture_desc_lm_img3d_val`)
+
+    :return tuple(ndarray,list(str)): features [nb_segments, nb_features], names
+    """
+    img, segments = np.asarray(img), np.asarray(segments)
+    _check_gray_image_segm(img, segments)
+    if not feature_flags:
+        raise ValueError('some features has to be selected')
+    features, names = [], []
+    if any(k.startswith('color') for k in feature_flags):
+        flags = np.unique([feature_flags[k] for k in feature_flags if k.startswith('color')])
+        fts, ns = compute_image3d_gray_statistic(img, segments, flags)
+        features.append(fts)
+        names += ns
+    for k in [k for k in feature_flags if k.startswith('tLM')]:
+        bank_type = k.split('_')[-1] if '_' in k else 'normal'
+        fts, ns = compute_texture_desc_lm_img3d_val(img, segments, feature_flags[k], bank_type)
+        features.append(fts)
+        names += ns
+    _check_unrecognised_feature_group(feature_flags)
+    if not features:
+        return np.array([[]] * (int(segments.max()) + 1)), []
+    features = np.nan_to_num(np.concatenate(tuple(features), axis=1))
+    features[features == 0] = 0          # -0 -> +0
+    if features.shape[1] != len(names):
+        raise ValueError('features: %r and names %r' % (features.shape, names))
+    return features, names
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# label histograms about positions (reference descriptors.py:1288-1528)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def adjust_bounding_box_crop(image_size, bbox_size, position):
+    """ the part of a box of ``bbox_size`` centred on ``position`` that lies inside an image, as index ranges of the image
+    and of the box (reference descriptors.py:1355-1393)
+
+    :return tuple: im_begin, im_end, bb_begin, bb_end
+    """
+    if len(image_size) != len(bbox_size):
+        raise ValueError('incompatible sizes %r != %r' % (image_size, bbox_size))
+    im_size, bb_size, pos = np.asarray(image_size), np.asarray(bbox_size), np.asarray(position)
+    half_lo, half_hi = np.floor(bb_size / 2.).astype(int), np.ceil(bb_size / 2.).astype(int)
+    im_begin = np.maximum(pos - half_lo, 0)
+    im_end = np.minimum(pos + half_hi, im_size)
+    bb_begin = np.where(im_begin == 0, half_lo - pos, 0)
+    bb_end = np.where(im_end == im_size, half_lo + (im_size - pos), bb_size)
+    if not np.array_equal(im_end - im_begin, bb_end - bb_begin):
+        raise ValueError('different sizes of image %r and bounding box %r mask' % (im_end - im_begin, bb_end - bb_begin))
+    return tuple(int(v) for v in im_begin), tuple(int(v) for v in im_end), tuple(int(v) for v in bb_begin), tuple(int(v) for v in bb_end)
+
+
+def _device_label_hists(segm, positions, nb_labels, diameters=None, struc_elem=None):
+    """label histograms under discs (``diameters``) or one explicit structuring element about every position, one launch
+    (``isb_disc_label_hist``).  ``segm`` is [H, W] labels or [H, W, K] per-label maps.
+    Returns (hist [n_pos, n_elems, nb_labels], sizes [n_pos, n_elems])."""
+    import ctypes as C
+    from . import _lib
+    segm = np.asarray(segm)
+    pos = np.ascontiguousarray(np.atleast_2d(np.asarray(positions)).astype(np.int32))
+    if pos.shape[1] != 2:
+        raise ValueError('positions have to be (row, col) pairs, got shape %r' % (pos.shape, ))
+    H, W = int(segm.shape[0]), int(segm.shape[1])
+    eng = get_engine()
+    torch = eng.torch
+    d_pos = eng.to_device(pos, 'hist_pos')
+    d_seg = d_proba = None
+    if segm.ndim == 2:
+        lab = np.array(segm, dtype=float)
+        lab[np.isnan(lab)] = -1
+        d_seg = eng.to_device(lab.astype(np.int32), 'hist_segm32')
+    else:
+        d_proba = eng.to_device(np.ascontiguousarray(segm, dtype=np.float64), 'hist_proba')
+    d_diam = d_sel = None
+    mh = mw = 0
+    if struc_elem is not None:
+        sel = np.ascontiguousarray(np.asarray(struc_elem) == 1, dtype=np.uint8)
+        mh, mw = int(sel.shape[0]), int(sel.shape[1])
+        d_sel = eng.to_device(sel, 'hist_selem8')
+        n_el = 1
+    else:
+        diam = np.ascontiguousarray(np.asarray(diameters, dtype=np.int32))
+        d_diam = eng.to_device(diam, 'hist_diam')
+        n_el = len(diam)
+    hist = eng.buf('hist_out64', (len(pos), n_el, int(nb_labels)), torch.float64)
+    sizes = eng.buf('hist_sizes', (len(pos), n_el), torch.float64)
+    _lib.check(eng.lib.isb_disc_label_hist(_lib.ptr(d_seg), _lib.ptr(d_proba), H, W, _lib.ptr(d_pos), len(pos), _lib.ptr(d_diam), n_el,
+                                           _lib.ptr(d_sel), mh, mw, int(nb_labels), _lib.ptr(hist), _lib.ptr(sizes), _lib.stream_ptr()))
+    return eng.to_host(hist).copy(), eng.to_host(sizes).copy()
+
+
+def _check_position_inside(shape, position):
+    if any(p < 0 or p >= s for p, s in zip(position, shape)):
+        raise ValueError('position %r lies outside the segmentation %r' % (position, tuple(shape)))
+
+
+def compute_label_hist_segm(segm, position, struc_elem, nb_labels):
+    """ histogram of the labels under a structuring element centred on ``position`` (reference descriptors.py:1396-1441)
+
+    :return tuple(ndarray,float): counts per label, number of element pixels inside the image
+    """
+    segm, struc_elem = np.asarray(segm), np.asarray(struc_elem)
+    if segm.ndim != len(position):
+        raise ValueError('dim of position %r should match the segmentation %r dim' % (position, segm.shape))
+    position = [int(p) for p in position]
+    _check_position_inside(segm.shape, position)
+    hist, sizes = _device_label_hists(segm, [position], nb_labels, struc_elem=struc_elem)
+    return hist[0, 0], struc_elem.dtype.type(sizes[0, 0])
+
+
+def compute_label_hist_proba(segm, position, struc_elem):
+    """ sums of the per-label maps ``segm[..., l]`` under a structuring element centred on ``position``
+    (reference descriptors.py:1501-1528)
+
+    :return tuple(ndarray,int): sums per label, number of element pixels inside the image
+    """
+    segm, struc_elem = np.asarray(segm), np.asarray(struc_elem)
+    if segm.ndim != (len(position) + 1):
+        raise ValueError('segment. (%r) should have larger (+1) dim than position %i' % (segm.shape, len(position)))
+    position = [int(p) for p in position]
+    _check_position_inside(segm.shape[:2], position)
+    hist, sizes = _device_label_hists(segm, [position], segm.shape[-1], struc_elem=struc_elem)
+    return hist[0, 0], struc_elem.dtype.type(sizes[0, 0])
+
+
+def compute_label_histograms_positions(segm, positions, diameters=HIST_CIRCLE_DIAGONALS, nb_labels=None):
+    """ label frequencies in concentric rings (discs of growing ``diameters`` minus the previous disc) about the positions
+    (reference descriptors.py:1288-1352); every disc of every position is counted in one kernel launch
+
+    :param ndarray segm: labels [H, W] or per-label maps [H, W, K]
+    :return tuple(ndarray,list(str)): features [nb_positions, nb_diameters * nb_labels], names
+    """
+    segm = np.asarray(segm)
+    pos_dim = np.asarray(positions).shape[1]
+    if (segm.ndim - pos_dim) not in (0, 1):
+        raise ValueError('dimension %r and %r difference should be 0 or 1' % (segm.ndim, pos_dim))
+    if nb_labels is None:
+        nb_labels = int(segm.max()) + 1 if segm.ndim == pos_dim else segm.shape[-1]
+    int_pos = [[int(p) for p in pos] for pos in positions]
+    for pos in int_pos:
+        _check_position_inside(segm.shape[:2], pos)
+    hist, sizes = _device_label_hists(segm, int_pos, nb_labels, diameters=list(diameters))
+    ring_size = np.diff(np.concatenate([np.zeros((len(int_pos), 1)), sizes], axis=1), axis=1)
+    if np.any(ring_size <= 0):
+        raise ValueError('norm or element should be positive')
+    ring_hist = np.diff(np.concatenate([np.zeros((len(int_pos), 1, nb_labels)), hist], axis=1), axis=1)
+    if np.any(ring_hist < 0):
+        raise ValueError('outer elem should have more labels then the inter')
+    pos_hists = (ring_hist / ring_size[:, :, None]).reshape(len(int_pos), -1)
+    feature_names = ['hist-d_%i-lb_%i' % (d, lb) for d in diameters for lb in range(nb_labels)]
+    if pos_hists.shape[1] != len(feature_names):
+        raise ValueError('histogram: %r and names %r' % (pos_hists.shape, feature_names))
+    return pos_hists, feature_names
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Ray features about positions (reference descriptors.py:1545-2041)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def numpy_ray_features_seg2d(seg_binary, position, angle_step=5., edge='up'):
+    """ the reference keeps a NumPy twin of its Cython ray tracer (descriptors.py:1663-1708); here both names run the CUDA kernel """
+    return cython_ray_features_seg2d(seg_binary, position, angle_step, edge)
+
+
+def _smooth_rays(ray_dist, smooth_coef):
+    if smooth_coef is not None and smooth_coef > 0:
+        from scipy.ndimage import gaussian_filter1d
+        return gaussian_filter1d(ray_dist, smooth_coef)
+    return ray_dist
+
+
+def compute_ray_features_segm_2d(seg_binary, position, angle_step=5., smooth_coef=0, edge='up'):
+    """ Ray features of one position: distance to the first boundary every ``angle_step`` degrees, optionally smoothed along
+    the angle (reference descriptors.py:1711-1759) """
+    seg_binary = np.asarray(seg_binary)
+    if seg_binary.ndim != len(position):
+        raise ValueError('Segmentation dim of %r and position (%i) does not match' % (seg_binary.ndim, len(position)))
+    ray_dist = cython_ray_features_seg2d(seg_binary.astype(bool), tuple(map(int, position)), angle_step, edge)
+    return _smooth_rays(ray_dist, smooth_coef)
+
+
+def shift_ray_features(ray_dist, method='phase'):
+    """ rotate a Ray feature vector to start at its dominant direction -- rotation invariance (reference descriptors.py:1762-1802)
+
+    :param str method: 'phase' (phase of the strongest Fourier component) or 'max' (largest distance)
+    :return tuple(ndarray,float): shifted vector, shift in degrees
+    """
+    ray_dist = np.asarray(ray_dist)
+    angle_step = 360 / len(ray_dist)
+    if method == 'phase':
+        ext = np.hstack([ray_dist] * 5)
+        spectrum = np.fft.fft(ext - np.mean(ext)) / float(len(ext))
+        half = len(ext) // 2
+        idx = np.argmax(np.abs(spectrum)[:half])
+        shift = np.rad2deg(-np.angle(spectrum)[:half][idx])
+        shift = (360 + shift) if shift < 0 else shift
+    else:
+        shift = float(np.argmax(ray_dist) * angle_step)
+    step = int(round(shift / angle_step))
+    return np.array(ray_dist[step:].tolist() + ray_dist[:step].tolist()), shift
+
+
+def compute_ray_features_positions(segm, list_positions, angle_step=5., border_labels=None, segm_open=None, smooth_ray=None,
+                                   shifting=True, edge='up'):
+    """ Ray features of many positions of a segmentation whose ``border_labels`` form the boundary
+    (reference descriptors.py:1805-1884); the rays of ALL positions are traced in one kernel launch
+
+    :return tuple(ndarray,list(float),list(str)): rays [nb_positions, nb_angles], shifts, names
+    """
+    segm = np.asarray(segm)
+    pos_dim = np.asarray(list_positions).shape[1]
+    if (segm.ndim - pos_dim) not in (0, 1):
+        raise ValueError('dimension %s and %s difference should be 0 or 1' % (segm.ndim, pos_dim))
+    border_labels = border_labels if border_labels is not None else [0]
+    if segm.ndim > pos_dim:
+        segm = np.argmax(segm, axis=-1)
+    if isinstance(segm_open, int):
+        raise NotImplementedError('segm_open (a morphological opening of the boundary mask, skimage.morphology.opening in the '
+                                  'reference) is not provided; open the mask beforehand')
+    seg_binary = np.isin(segm, list(border_labels))
+    positions = [tuple(map(int, pos)) for pos in list_positions]
+    rays = np.atleast_2d(cython_ray_features_seg2d(seg_binary, np.asarray(positions), angle_step, edge))
+    pos_rays, pos_shift = [], []
+    for ray_dist in rays:
+        ray_dist = _smooth_rays(ray_dist, smooth_ray)
+        shift = 0
+        if shifting:
+            ray_dist, shift = shift_ray_features(ray_dist)
+        pos_rays.append(ray_dist)
+        pos_shift.append(float(shift))
+    nb_rays = rays.shape[1]
+    feature_names = ['ray-lb_%s-agl_%i' % (''.join(map(str, border_labels)), int(a)) for a in np.linspace(0, 360 - angle_step, nb_rays)]
+    pos_rays = np.array(pos_rays)
+    if pos_rays.shape[1] != len(feature_names):
+        raise ValueError('Ray features: %r and names %r' % (pos_rays.shape, feature_names))
+    return pos_rays, pos_shift, feature_names
+
+
+def interpolate_ray_dist(ray_dists, order='spline'):
+    """ fill the missing (-1) entries of a periodic Ray vector (reference descriptors.py:1887-1951)
+
+    :param str|int order: polynomial degree, 'spline' (periodic interpolating spline) or 'cos' (fitted sinusoid)
+    """
+    ray_dists = np.array(ray_dists)
+    x_space = np.arange(len(ray_dists))
+    missing = ray_dists == -1
+    x_train, y_train = x_space[~missing], ray_dists[~missing]
+    if not y_train.size:
+        return ray_dists
+    if isinstance(order, int):
+        ray_dists[missing] = np.poly1d(np.polyfit(x_train, y_train, order))(x_space[missing])
+    elif order == 'spline':
+        from scipy import interpolate
+        n = len(x_space)
+        spline = interpolate.InterpolatedUnivariateSpline(np.hstack((x_train - n, x_train, x_train + n)), np.tile(y_train, 3))
+        ray_dists[missing] = spline(x_space[missing])
+    elif order == 'cos':
+        from scipy import optimize
+
+        def _wave(x, t):
+            return x[0] + x[1] * np.sin(x[2] + x[3] * t)
+
+        x0 = np.array([np.mean(y_train), (y_train.max() - y_train.min()) / 2., 0, len(x_space) / np.pi])
+        fit = optimize.least_squares(lambda x, t, y: _wave(x, t) - y, x0, gtol=1e-1, args=(x_train, y_train))
+        ray_dists[missing] = _wave(fit.x, x_space[missing])
+    return ray_dists
+
+
+def reconstruct_ray_features_2d(position, ray_features, shift=0):
+    """ the boundary points a Ray vector describes about ``position`` (reference descriptors.py:1954-1999)
+
+    :return ndarray: points [nb_valid_rays, 2]
+    """
+    if len(position) != 2:
+        raise ValueError('positions has to have 2 coordinates')
+    if len(ray_features) <= 2:
+        raise ValueError('required at least 2 features')
+    ray_features = np.asarray(ray_features)
+    angles = (np.pi / 2.) - np.linspace(0, 2 * np.pi, len(ray_features), endpoint=False) - np.deg2rad(shift)
+    valid = np.logical_and(ray_features >= 0, ~np.isinf(ray_features))
+    angles, rays = angles[valid], ray_features[valid]
+    return np.tile(position, (len(rays), 1)) + np.array([np.cos(angles) * rays, np.sin(angles) * rays]).T
+
+
+def reduce_close_points(points, dist_thr):
+    """ drop points until no two of them are closer than ``dist_thr``; of the closest pair the later one goes
+    (reference descriptors.py:2002-2041) """
+    if len(points) <= 2:
+        raise ValueError('too few point to be reduced')
+    from scipy import spatial
+    points = np.asarray(points)
+    dist = spatial.distance.cdist(points, points, metric='euclidean')
+    np.fill_diagonal(dist, np.inf)
+    while len(points) > 0 and dist.size and np.min(dist) < dist_thr:
+        drop = max(np.unravel_index(dist.argmin(), dist.shape))
+        points = np.delete(points, drop, axis=0)
+        dist = np.delete(np.delete(dist, drop, axis=0), drop, axis=1)
+    return points
+
+
 def compute_image2d_color_statistic(image, segm, feature_flags=NAMES_FEATURE_FLAGS, color_name='color'):
     """ statistics of a colour image over the segments; columns are statistic-major, channel-minor
     (reference descriptors.py:787-863)
@@ -350,3 +846,8 @@ def native_feature_layout(dict_features):
         layout.append((k, flags, col, n))
         col += n
     return layout, col
+
+
+# the Leung-Malik bank lives in texture.py (it shares the device layout code); the reference keeps it in this module
+from .texture import (compute_texture_desc_lm_img2d_clr, create_filter_bank_lm_2d, make_edge_filter2d,  # noqa: E402,F401
+                      make_gaussian_filter1d)

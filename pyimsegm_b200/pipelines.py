@@ -26,6 +26,8 @@ from .superpixels import _as_rgb_like, _supported_dtype, slic_params
 #: basic features extracted from superpixels (reference pipelines.py:35)
 FTS_SET_SIMPLE = FEATURES_SET_COLOR
 #: default clustering for unsupervised segmentation (reference pipelines.py:39 -> classification.DEFAULT_CLUSTERING)
+#: default classifier of the supervised path (reference classification.py:54; the classifier zoo itself is out of scope)
+CLASSIF_NAME = 'RandForest'
 CLUSTER_METHOD = 'kMeans'
 #: images left out during cross-validation training (reference pipelines.py:41)
 CROSS_VAL_LEAVE_OUT = 2
@@ -297,6 +299,51 @@ def segment_images_batch(list_images, nb_classes=None, dict_features=FTS_SET_SIM
     while pending:
         _finish(pending.pop(0))
     return results
+
+
+def wrapper_compute_color2d_slic_features_labels(img_annot, sp_size, sp_regul, dict_features, label_purity):
+    """ superpixels, their features and one training label per superpixel from an annotated image -- the data step of the
+    supervised path (reference pipelines.py:272-290): a superpixel takes the annotation label that covers most of it, or -1
+    when that share is below ``label_purity`` (or the winner is the negative / unknown label)
+
+    :param tuple(ndarray,ndarray) img_annot: image and its annotation (negative values = unknown)
+    :return tuple(ndarray,ndarray,ndarray): slic [H, W], features [N, D], labels [N]
+    """
+    from .labeling import histogram_regions_labels_norm
+    from .utilities import ImageDimensionError
+    img, annot = img_annot
+    annot = np.asarray(annot).astype(int)
+    if np.shape(img)[:2] != annot.shape[:2]:
+        raise ImageDimensionError('image %r and annot %r should match' % (np.shape(img), annot.shape))
+    slic, features = compute_color2d_superpixels_features(img, dict_features, sp_size=sp_size, sp_regul=sp_regul)
+    neg_label = int(np.max(annot)) + 1 if np.any(annot < 0) else None
+    if neg_label is not None:
+        annot = np.where(annot < 0, neg_label, annot)
+    label_hist = histogram_regions_labels_norm(slic, annot)       # joint histogram on the device (isb_region_label_hist)
+    labels = np.argmax(label_hist, axis=1)
+    purity = np.max(label_hist, axis=1)
+    if neg_label is not None:
+        labels[labels == neg_label] = -1
+    labels[purity < label_purity] = -1
+    return slic, features, labels
+
+
+def train_classif_color2d_slic_features(list_images, list_annots, dict_features, sp_size=30, sp_regul=0.2, clf_name=CLASSIF_NAME,
+                                        label_purity=0.9, feature_balance='unique', pca_coef=None, nb_classif_search=1,
+                                        nb_hold_out=CROSS_VAL_LEAVE_OUT, nb_workers=1):
+    """ the supervised training wrapper of the reference (pipelines.py:293-379).  Its data step is available here
+    (:func:`wrapper_compute_color2d_slic_features_labels`); the classifier zoo, hyper-parameter search and dataset balancing it
+    hands the data to (``imsegm/classification.py``) are outside the accelerated hot path """
+    raise NotImplementedError('supervised classifier training (imsegm.classification) is outside the B200 hot path; '
+                              'use wrapper_compute_color2d_slic_features_labels for the features and labels')
+
+
+def pipe_gray3d_slic_features_model_graphcut(image, nb_classes, dict_features, spacing=(12, 1, 1), sp_size=15, sp_regul=0.2,
+                                             gc_regul=0.1):
+    """ the gray-volume variant of the pipeline (reference pipelines.py:382-431): needs the 3-D SLIC of
+    ``superpixels.segment_slic_img3d_gray``, which is not part of the accelerated hot path yet (SURVEY.md section 8f, rank 3);
+    the gray-volume statistics (``descriptors.compute_selected_features_gray3d``) and the graph cut are """
+    raise NotImplementedError('3-D gray SLIC is outside the B200 hot path (SURVEY.md section 8f, rank 3)')
 
 
 def segment_resident(d_image, model, dict_features, sp_size=30, sp_regul=0.2, gc_regul=1., gc_edge_type='model'):

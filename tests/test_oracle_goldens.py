@@ -171,3 +171,65 @@ def test_alpha_expansion_is_a_local_minimum_and_matches_brute_force(oracle):
             assert energy == best     # one expansion on a binary Potts problem is the global optimum
         else:
             assert energy <= 2 * best  # expansion's approximation bound for a metric
+
+
+def test_label_histograms_reference_doctests(oracle):
+    """imsegm/descriptors.py:1301-1325, :1406-1424, :1511-1516 -- the goldens of the label-histogram drivers"""
+    segm = np.zeros((10, 10), dtype=int)
+    segm[1:9, 2:8] = 1
+    segm[3:7, 4:6] = 2
+    points = [[3, 3], [4, 4], [2, 7], [6, 6]]
+    want = np.array([[0., 0.8, 0.2, 0.12, 0.62, 0.25, 0.44, 0.41, 0.15], [0., 0.2, 0.8, 0., 0.62, 0.38, 0.22, 0.75, 0.03],
+                     [0.2, 0.8, 0., 0.5, 0.5, 0., 0.46, 0.33, 0.21], [0., 0.8, 0.2, 0.12, 0.62, 0.25, 0.44, 0.41, 0.15]])
+    assert np.array_equal(np.round(oracle.label_histograms_positions(segm, points, [1, 2, 4]), 2), want)
+    proba = np.zeros((10, 10, 2), dtype=int)
+    proba[3:7, 4:6, 1] = 1
+    proba[:, :, 0] = 1 - proba[:, :, 0]
+    want = np.array([[1., 0.2, 1., 0.25, 1., 0.15], [1., 0.8, 1., 0.38, 1., 0.03], [1., 0., 1., 0., 1., 0.21], [1., 0.2, 1., 0.25, 1., 0.15]])
+    assert np.array_equal(np.round(oracle.label_histograms_positions(proba, points, [1, 2, 4]), 2), want)
+    hist, size = oracle.label_hist_selem(segm, [6, 6], np.ones((3, 3)), 3)
+    assert hist.tolist() == [0., 7., 2.] and size == 9
+    hist, size = oracle.label_hist_selem(segm, [4, 4], np.ones((5, 5)), 3)
+    assert hist.tolist() == [0., 17., 8.] and size == 25
+    seg = np.zeros((50, 50, 2), dtype=float)
+    seg[15:35, 20:40, 1] = 1
+    seg[:, :, 0] = 1 - seg[:, :, 1]
+    hist, size = oracle.label_hist_selem(seg, (15, 20), np.ones((12, 13), dtype=int))
+    assert hist.tolist() == [114., 42.] and size == 156
+
+
+def test_host_side_descriptor_helpers_reference_doctests():
+    """pure-host helpers of the Ray / histogram drivers against the reference's doctest values
+    (imsegm/descriptors.py:1380-1387, :1773-1786, :1905-1920, :1975-1983, :2013-2025)"""
+    from pyimsegm_b200 import descriptors as ds
+    assert ds.adjust_bounding_box_crop((50, 50), (7, 7), (20, 20)) == ((17, 17), (24, 24), (0, 0), (7, 7))
+    assert ds.adjust_bounding_box_crop((50, 50), (15, 15), (20, 45)) == ((13, 38), (28, 50), (0, 0), (15, 12))
+    assert ds.adjust_bounding_box_crop((50, 50), (15, 15), (5, 5)) == ((0, 0), (13, 13), (2, 2), (15, 15))
+    assert ds.adjust_bounding_box_crop((50, 50), (80, 80), (20, 20)) == ((0, 0), (50, 50), (20, 20), (70, 70))
+    vec = np.array([43, 46, 44, 39, 28, 18, 12, 10, 9, 12, 22, 28])
+    ray, shift = ds.shift_ray_features(vec)
+    assert abs(shift - 41.50) < 0.01 and ray.tolist() == [46, 44, 39, 28, 18, 12, 10, 9, 12, 22, 28, 43]
+    ray2, shift2 = ds.shift_ray_features(ray)
+    assert abs(shift2 - 11.50) < 0.01 and np.array_equal(ray, ray2)
+    assert ds.shift_ray_features(vec, method='max')[1] == 30.0
+    assert ds.interpolate_ray_dist([-1] * 5).tolist() == [-1] * 5
+    vals = np.sin(np.linspace(0, 2 * np.pi, 20)) * 10
+    vals[3:7] = -1
+    vals[16:] = -1
+    assert np.round(ds.interpolate_ray_dist(vals, order='spline')).astype(int).tolist() == \
+        [0, 3, 6, 8, 9, 10, 9, 7, 5, 2, -2, -5, -7, -9, -10, -10, -9, -7, -5, -3]
+    assert np.round(ds.interpolate_ray_dist(vals, order='cos')).astype(int).tolist() == \
+        [0, 3, 6, 8, 10, 10, 9, 7, 5, 2, -2, -5, -7, -9, -10, -10, -8, -6, -3, 0]
+    np.testing.assert_allclose(ds.reconstruct_ray_features_2d((10., 10), np.array([1] * 4)), [[10, 11], [11, 10], [10, 9], [9, 10]], atol=1e-12)
+    np.testing.assert_allclose(ds.reconstruct_ray_features_2d((10., 10), np.array([-1, 0, 1, np.inf])), [[10, 10], [10, 9]], atol=1e-12)
+    assert ds.reduce_close_points(np.array([range(10), range(10)]).T, 2).tolist() == [[0, 0], [2, 2], [4, 4], [6, 6], [8, 8]]
+    assert ds.reduce_close_points(np.array([[0, 0], [1, 1], [0, 2]]), 2).tolist() == [[0, 0], [0, 2]]
+    assert ds.reduce_close_points(np.ones((10, 2)), 2).tolist() == [[1., 1.]]
+    # the NumPy variants of the gray-volume statistics (descriptors.py:545-676) on the doctest volume of :698-715
+    img = np.array([[[0] * 3 + [1] * 3 + [2] * 2] * 3] * 2, dtype=float)[:, :, :8]
+    seg = np.array([[[0] * 2 + [1] * 2 + [2] * 2 + [5] * 2] * 3] * 2)
+    assert ds.numpy_img3d_gray_mean(img, seg).shape == (6, )
+    np.testing.assert_allclose(ds.numpy_img3d_gray_mean(img, seg)[[0, 1, 2, 5]], [0., 0.5, 1., 2.])
+    np.testing.assert_allclose(ds.numpy_img3d_gray_std(img, seg)[[0, 1, 2, 5]], [0., 0.5, 0., 0.])
+    np.testing.assert_allclose(ds.numpy_img3d_gray_energy(img, seg)[[0, 1, 2, 5]], [0., 0.5, 1., 4.])
+    np.testing.assert_allclose(ds.numpy_img3d_gray_median(img, seg)[[0, 1, 2, 5]], [0., 0.5, 1., 2.])
