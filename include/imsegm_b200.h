@@ -108,11 +108,30 @@ int isb_slic_band_finalize(const isb_slic_band_t* band, const uint64_t* maxdc_xc
 
 size_t isb_connectivity_workspace_bytes(int H, int W);
 
+
 /* _enforce_label_connectivity_cython: raster-order relabel of 4-connected components, BFS truncated at max_size,
  * components < min_size merged into the last already-labelled neighbour seen.  Bit-exact with the oracle.
  *   n_labels_out : device int32, number of output labels (labels are 0..n-1) */
 int isb_enforce_connectivity(const int32_t* labels, int H, int W, int min_size, int max_size, int32_t* out,
                              int32_t* n_labels_out, void* ws, size_t ws_bytes, isb_stream_t stream);
+
+/* SLIC of a single-channel VOLUME -- replaces skimage.segmentation.slic(vol, n_segments, compactness, multichannel=False,
+ * spacing=space, sigma=1) as called from imsegm/superpixels.py:104-106 (segment_slic_img3d_gray).  Bit-exact with
+ * oracle/slic3d_oracle.c.  Written for generality (the reference's volumes are small), see csrc/slic3d.cu.
+ *   isb_slic3d_prepare : dtype -> f64 (img_as_float scale for the integer types), scipy gaussian_filter along z, y, x with the
+ *                        DEVICE half kernels w_* (radius + 1 weights, [0] = centre; radius 0 / weight 1 = axis not blurred),
+ *                        then * ratio (= 1 / compactness).  tmp: scratch of D*H*W doubles
+ *   isb_slic3d_kmeans  : the sweeps of _slic_cython; seeds_zyx [n,3] (device); spacing_host: 3 HOST doubles (z, y, x) */
+int isb_slic3d_prepare(const void* vol, int dtype, int D, int H, int W, const double* w_z, int r_z, const double* w_y, int r_y,
+                       const double* w_x, int r_x, double ratio, double* tmp, double* out, isb_stream_t stream);
+size_t isb_slic3d_kmeans_workspace_bytes(int D, int H, int W, int n_seeds);
+int isb_slic3d_kmeans(const double* vol_scaled, int D, int H, int W, const double* seeds_zyx, int n_seeds, int step_z, int step_y,
+                      int step_x, double step, const double* spacing_host, int max_iter, int32_t* labels, void* ws, size_t ws_bytes,
+                      isb_stream_t stream);
+/* _enforce_label_connectivity_cython on a volume (6 neighbours in the order x+1, x-1, y+1, y-1, z+1, z-1) */
+size_t isb_connectivity3d_workspace_bytes(int D, int H, int W, int max_size);
+int isb_enforce_connectivity3d(const int32_t* labels, int D, int H, int W, int min_size, int max_size, int32_t* out,
+                               int32_t* n_labels_out, void* ws, size_t ws_bytes, isb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * (ii) descriptors -- replaces imsegm/features_cython.pyx (the reference's only native module)
@@ -198,6 +217,13 @@ int isb_ray_features_2d(const int8_t* seg_binary, int H, int W, const int32_t* p
 size_t isb_adjacency_workspace_bytes(int nb, int cap);
 int isb_adjacency_edges(const int32_t* seg, int H, int W, int nb, int32_t* edges, int cap, int32_t* n_edges_out, void* ws,
                         size_t ws_bytes, isb_stream_t stream);
+
+/* the same for a label VOLUME [D, H, W]: 6-connectivity (make_graph_segm_connect_grid3d_conn6, superpixels.py:180-202); same
+ * workspace as isb_adjacency_edges.  isb_centroids_3d: centre (z, y, x) of every label, (-1,-1,-1) when absent
+ * (superpixel_centers on a volume); ws: 4 * nb uint64 */
+int isb_adjacency_edges_3d(const int32_t* seg, int D, int H, int W, int nb, int32_t* edges, int cap, int32_t* n_edges_out, void* ws,
+                           size_t ws_bytes, isb_stream_t stream);
+int isb_centroids_3d(const int32_t* seg, int D, int H, int W, int nb, double* centres, void* ws, size_t ws_bytes, isb_stream_t stream);
 
 /* compute_unary_cost (imsegm/graph_cuts.py:523-540), compute_edge_weights / compute_edge_model / compute_spatial_dist
  * (:574-657, :383-439, :303-336), create_pairwise_matrix_uniform (:442-456), and pyGCO's float->int conversion.

@@ -26,7 +26,7 @@ _LIB = None
 def build(force=False):
     """compile oracle/liboracle.so (and oracle/_ref when /root/reference exists) with the committed Makefile"""
     so = os.path.join(_HERE, 'liboracle.so')
-    srcs = [os.path.join(_HERE, f) for f in ('slic_oracle.c', 'stats_oracle.c', 'gc_oracle.cpp')]
+    srcs = [os.path.join(_HERE, f) for f in ('slic_oracle.c', 'slic3d_oracle.c', 'stats_oracle.c', 'gc_oracle.cpp')]
     stale = (not os.path.isfile(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
         subprocess.check_call(['make', '-C', _HERE, 'liboracle.so'], stdout=subprocess.DEVNULL)
@@ -48,6 +48,7 @@ def lib():
         _LIB.oracle_det_pow24.restype = C.c_double
         _LIB.oracle_det_pow24.argtypes = [C.c_double]
         _LIB.oracle_enforce_connectivity.restype = C.c_int64
+        _LIB.oracle_enforce_connectivity3d.restype = C.c_int64
     return _LIB
 
 
@@ -476,3 +477,67 @@ def label_histograms_positions(segm, positions, diameters, nb_labels=None):
             last_h, last_s = h, sz
         rows.append(row)
     return np.array(rows)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 3-D gray SLIC (imsegm/superpixels.py:72-112 -> skimage slic(multichannel=False, spacing, sigma=1)) -- slic3d_oracle.c
+# ---------------------------------------------------------------------------------------------------------------------
+
+def slic_seeds3d(shape, n_segments):
+    (sz, tz), (sy, ty), (sx, tx) = regular_grid(shape, n_segments)
+    gz, gy, gx = np.meshgrid(np.arange(sz, shape[0], tz), np.arange(sy, shape[1], ty), np.arange(sx, shape[2], tx), indexing='ij')
+    seeds = np.stack([gz.ravel(), gy.ravel(), gx.ravel()], axis=1).astype(np.float64)
+    return np.ascontiguousarray(seeds), (int(tz), int(ty), int(tx))
+
+
+def gaussian_blur3d(vol, sigmas):
+    vol = np.ascontiguousarray(vol, dtype=np.float64)
+    D, H, W = vol.shape
+    halves = []
+    for s in sigmas:
+        halves.append(gaussian_weights(float(s)) if s > 0 else (np.ones(1), 0))
+    out = np.empty_like(vol)
+    rc = lib().oracle_gaussian_blur3d(_p(vol, C.c_double), D, H, W, _p(halves[0][0], C.c_double), int(halves[0][1]),
+                                      _p(halves[1][0], C.c_double), int(halves[1][1]), _p(halves[2][0], C.c_double), int(halves[2][1]),
+                                      _p(out, C.c_double))
+    assert rc == 0
+    return out
+
+
+def slic3d(vol, n_segments, compactness, spacing=(1, 1, 1), sigma=1.0, max_iter=10, enforce_conn=True, min_size_factor=0.5,
+           max_size_factor=3, return_kmeans=False):
+    """skimage.segmentation.slic(vol, n_segments, compactness, multichannel=False, spacing=spacing, sigma=sigma), 0.14-0.18"""
+    scale = {'uint8': 255.0, 'uint16': 65535.0}.get(str(np.asarray(vol).dtype))      # img_as_float
+    vol = np.ascontiguousarray(vol, dtype=np.float64)
+    if scale:
+        vol = vol / scale
+    D, H, W = vol.shape
+    spacing = np.ascontiguousarray(spacing, dtype=np.float64)
+    if sigma > 0:
+        vol = gaussian_blur3d(vol, np.array([sigma, sigma, sigma], dtype=np.float64) / spacing)
+    seeds, (tz, ty, tx) = slic_seeds3d((D, H, W), n_segments)
+    step = float(max(tz, ty, tx))
+    scaled = np.ascontiguousarray(vol * (1.0 / compactness))
+    labels = np.empty((D, H, W), dtype=np.int64)
+    lib().oracle_slic_kmeans3d(_p(scaled, C.c_double), D, H, W, _p(seeds, C.c_double), len(seeds), tz, ty, tx, C.c_double(step),
+                               _p(spacing, C.c_double), int(max_iter), _p(labels, C.c_int64), None)
+    if return_kmeans or not enforce_conn:
+        return labels
+    segment_size = D * H * W / n_segments
+    out = np.empty_like(labels)
+    n = lib().oracle_enforce_connectivity3d(_p(labels, C.c_int64), D, H, W, C.c_long(int(min_size_factor * segment_size)),
+                                            C.c_long(int(max_size_factor * segment_size)), _p(out, C.c_int64))
+    assert n >= 0
+    return out
+
+
+def segment_slic_img3d_gray(im, sp_size=50, relative_compact=0.1, space=(1, 1, 1)):
+    """imsegm/superpixels.py:72-112.  The closing skimage.measure.label (:111, full connectivity, background 0) renumbers the
+    labels in the order of their first voxel and leaves label 0 alone; the connectivity pass already numbers the labels in
+    that order, so it changes nothing (checked in tests/test_oracle_goldens.py with scipy.ndimage.label)."""
+    im = np.asarray(im)
+    nb_pixels = np.prod(im.shape)
+    size = np.prod(sp_size / np.asarray(space, dtype=np.float32) * min(space))
+    n_seg = int(nb_pixels / size)
+    compact = int((size * relative_compact) ** 1.5)
+    return slic3d(np.array(im), n_seg, compact, space, sigma=1)

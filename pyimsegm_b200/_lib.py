@@ -51,12 +51,19 @@ SIGNATURES = {
     'isb_segment_stats_finish': (_i, [_i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     'isb_slic_kmeans_workspace_bytes': (_sz, [_i, _i, _i, _i, _i]),
     'isb_slic_kmeans': (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    'isb_slic3d_prepare': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _d, _vp, _vp, _vp]),
+    'isb_slic3d_kmeans_workspace_bytes': (_sz, [_i, _i, _i, _i]),
+    'isb_slic3d_kmeans': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _d, C.POINTER(_d), _i, _vp, _vp, _sz, _vp]),
+    'isb_connectivity3d_workspace_bytes': (_sz, [_i, _i, _i, _i]),
+    'isb_enforce_connectivity3d': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     'isb_connectivity_workspace_bytes': (_sz, [_i, _i]),
     'isb_enforce_connectivity': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     'isb_segment_stats_workspace_bytes': (_sz, [_i]),
     'isb_segment_stats_2d': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     'isb_adjacency_workspace_bytes': (_sz, [_i, _i]),
     'isb_adjacency_edges': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    'isb_adjacency_edges_3d': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    'isb_centroids_3d': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     'isb_gc_energies_workspace_bytes': (_sz, [_i, _i, _i]),
     'isb_gc_energies': (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'isb_alpha_expansion_workspace_bytes': (_sz, [_i, _i, _i]),

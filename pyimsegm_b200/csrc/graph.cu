@@ -67,6 +67,36 @@ __global__ void __launch_bounds__(256) k_edge_scan(const int* __restrict__ seg, 
     }
 }
 
+// the same for a volume: 6-connectivity = the pairs with the x+1, y+1 and z+1 neighbour (reference superpixels.py:145-154)
+__global__ void __launch_bounds__(256) k_edge_scan3d(const int* __restrict__ seg, int D, int H, int W, AdjWs w)
+{
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (size_t)D * H * W) return;
+    const int x = (int)(p % W), y = (int)((p / W) % H), z = (int)(p / ((size_t)H * W));
+    const int l = seg[p];
+    if (x + 1 < W) { const int r = seg[p + 1]; if (r != l) edge_insert(w, l, r); }
+    if (y + 1 < H) { const int d = seg[p + W]; if (d != l) edge_insert(w, l, d); }
+    if (z + 1 < D) { const int b = seg[p + (size_t)H * W]; if (b != l) edge_insert(w, l, b); }
+}
+
+// centroids (z, y, x) of the labels of a volume, (-1, -1, -1) for absent labels (superpixels.py:205-242 for 3-D input)
+__global__ void k_centroid3d_acc(const int* __restrict__ seg, int D, int H, int W, unsigned long long* acc)
+{
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (size_t)D * H * W) return;
+    const int x = (int)(p % W), y = (int)((p / W) % H), z = (int)(p / ((size_t)H * W));
+    unsigned long long* a = acc + 4 * (size_t)seg[p];
+    atomicAdd(a, 1ull); atomicAdd(a + 1, (unsigned long long)z); atomicAdd(a + 2, (unsigned long long)y); atomicAdd(a + 3, (unsigned long long)x);
+}
+
+__global__ void k_centroid3d_fin(int nb, const unsigned long long* acc, double* centres)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nb) return;
+    const double c = (double)acc[4 * (size_t)k];
+    for (int d = 0; d < 3; ++d) centres[3 * (size_t)k + d] = c > 0 ? (double)acc[4 * (size_t)k + 1 + d] / c : -1.0;
+}
+
 // exclusive scan of deg -> off (single CTA)
 __global__ void __launch_bounds__(1024) k_edge_offsets(int nb, AdjWs w, int cap, int* n_edges_out)
 {
@@ -285,6 +315,46 @@ extern "C" int isb_adjacency_edges(const int32_t* seg, int H, int W, int nb, int
     k_edge_fill<<<(w.slots + 255) / 256, 256, 0, st>>>(w, cap);
     ISB_LAUNCH_CHECK();
     k_edge_emit<<<(nb + 127) / 128, 128, 0, st>>>(nb, w, cap, edges);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
+extern "C" int isb_adjacency_edges_3d(const int32_t* seg, int D, int H, int W, int nb, int32_t* edges, int cap, int32_t* n_edges_out,
+                                      void* ws, size_t ws_bytes, isb_stream_t stream)
+{
+    ISB_REQUIRE(seg && edges && n_edges_out && ws, "null pointer");
+    ISB_REQUIRE(D > 0 && H > 0 && W > 0 && nb > 0 && cap > 0, "bad sizes");
+    AdjWs w;
+    size_t need = carve_adj(w, ws, ws_bytes, nb, cap);
+    ISB_REQUIRE(need <= ws_bytes, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ISB_PROF_ADJ, st);
+    ISB_CUDA_CHECK(cudaMemsetAsync(w.table, 0xFF, sizeof(unsigned long long) * (size_t)w.slots, st));
+    ISB_CUDA_CHECK(cudaMemsetAsync(w.deg, 0, sizeof(int) * (size_t)nb, st));
+    ISB_CUDA_CHECK(cudaMemsetAsync(w.ctr, 0, sizeof(int) * 4, st));
+    size_t n = (size_t)D * H * W;
+    k_edge_scan3d<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(seg, D, H, W, w);
+    ISB_LAUNCH_CHECK();
+    k_edge_offsets<<<1, 1024, 0, st>>>(nb, w, cap, n_edges_out);
+    ISB_LAUNCH_CHECK();
+    k_edge_fill<<<(w.slots + 255) / 256, 256, 0, st>>>(w, cap);
+    ISB_LAUNCH_CHECK();
+    k_edge_emit<<<(nb + 127) / 128, 128, 0, st>>>(nb, w, cap, edges);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
+extern "C" int isb_centroids_3d(const int32_t* seg, int D, int H, int W, int nb, double* centres, void* ws, size_t ws_bytes, isb_stream_t stream)
+{
+    ISB_REQUIRE(seg && centres && ws, "null pointer");
+    ISB_REQUIRE(D > 0 && H > 0 && W > 0 && nb > 0, "bad sizes");
+    ISB_REQUIRE(ws_bytes >= sizeof(unsigned long long) * 4 * (size_t)nb, "workspace too small (4 * nb uint64)");
+    cudaStream_t st = (cudaStream_t)stream;
+    ISB_CUDA_CHECK(cudaMemsetAsync(ws, 0, sizeof(unsigned long long) * 4 * (size_t)nb, st));
+    size_t n = (size_t)D * H * W;
+    k_centroid3d_acc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(seg, D, H, W, (unsigned long long*)ws);
+    ISB_LAUNCH_CHECK();
+    k_centroid3d_fin<<<(nb + 255) / 256, 256, 0, st>>>(nb, (const unsigned long long*)ws, centres);
     ISB_LAUNCH_CHECK();
     return ISB_OK;
 }

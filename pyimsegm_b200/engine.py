@@ -57,6 +57,14 @@ def slic_seed_grid(H, W, n_segments):
     return np.ascontiguousarray(seeds), int(ty), int(tx)
 
 
+def slic_seed_grid3d(shape, n_segments):
+    """seeds (z, y, x) of skimage's regular grid over a volume and the per-axis steps"""
+    (sz, tz), (sy, ty), (sx, tx) = regular_grid_steps(shape, n_segments)
+    gz, gy, gx = np.meshgrid(np.arange(sz, shape[0], tz), np.arange(sy, shape[1], ty), np.arange(sx, shape[2], tx), indexing='ij')
+    seeds = np.stack([gz.ravel(), gy.ravel(), gx.ravel()], axis=1).astype(np.float64)
+    return np.ascontiguousarray(seeds), (int(tz), int(ty), int(tx))
+
+
 class Engine(object):
     """owns the device buffers for one image shape at a time and sequences the C-ABI calls on the current stream"""
 
@@ -146,6 +154,62 @@ class Engine(object):
         self._ck(lib.isb_enforce_connectivity(_lib.ptr(km), H, W, min_size, max_size, _lib.ptr(out), _lib.ptr(n_labels),
                                               _lib.ptr(cws), C.c_size_t(cwsb), st))
         return out, n_labels
+
+    def slic3d(self, d_vol, n_segments, compactness, spacing=(1, 1, 1), sigma=1.0, max_iter=10, enforce_connectivity=True,
+               min_size_factor=0.5, max_size_factor=3):
+        """device SLIC of a single-channel volume [D, H, W] (csrc/slic3d.cu); returns (labels int32 [D,H,W], n_labels or None)"""
+        torch, lib = self.torch, self.lib
+        D, H, W = (int(v) for v in d_vol.shape)
+        code = _lib.DTYPE_CODES[str(d_vol.dtype).replace('torch.', '')]
+        st = _lib.stream_ptr()
+        spacing = np.ascontiguousarray(spacing, dtype=np.float64)
+        halves = []
+        for axis, sig in enumerate(np.array([sigma, sigma, sigma], dtype=np.float64) / spacing):
+            w_half, radius = gaussian_half_kernel(sig) if sigma > 0 else (np.ones(1), 0)
+            halves.append((self.to_device(w_half, 'slic3d_w%d' % axis), radius))
+        tmp = self.buf('slic3d_tmp', (D, H, W), torch.float64)
+        scaled = self.buf('slic3d_vol', (D, H, W), torch.float64)
+        self._ck(lib.isb_slic3d_prepare(_lib.ptr(d_vol), code, D, H, W, _lib.ptr(halves[0][0]), halves[0][1], _lib.ptr(halves[1][0]),
+                                        halves[1][1], _lib.ptr(halves[2][0]), halves[2][1], C.c_double(1.0 / compactness), _lib.ptr(tmp),
+                                        _lib.ptr(scaled), st))
+        seeds, steps = slic_seed_grid3d((D, H, W), n_segments)
+        n_seeds = len(seeds)
+        d_seeds = self.to_device(seeds, 'seeds3d')
+        wsb = lib.isb_slic3d_kmeans_workspace_bytes(D, H, W, n_seeds)
+        ws = self.buf('ws_kmeans3d', (wsb,), torch.uint8)
+        km = self.buf('labels_km3d', (D, H, W), torch.int32)
+        self._ck(lib.isb_slic3d_kmeans(_lib.ptr(scaled), D, H, W, _lib.ptr(d_seeds), n_seeds, steps[0], steps[1], steps[2],
+                                       C.c_double(float(max(steps))), spacing.ctypes.data_as(C.POINTER(C.c_double)), int(max_iter),
+                                       _lib.ptr(km), _lib.ptr(ws), C.c_size_t(wsb), st))
+        if not enforce_connectivity:
+            return km, None
+        segment_size = D * H * W / n_segments
+        min_size, max_size = int(min_size_factor * segment_size), int(max_size_factor * segment_size)
+        cwsb = lib.isb_connectivity3d_workspace_bytes(D, H, W, max(max_size, 1))
+        cws = self.buf('ws_conn3d', (cwsb,), torch.uint8)
+        out = self.buf('labels3d', (D, H, W), torch.int32)
+        n_labels = self.buf('n_labels', (1,), torch.int32)
+        self._ck(lib.isb_enforce_connectivity3d(_lib.ptr(km), D, H, W, min_size, max_size, _lib.ptr(out), _lib.ptr(n_labels), _lib.ptr(cws),
+                                                C.c_size_t(cwsb), st))
+        return out, n_labels
+
+    def graph3d(self, d_seg, nb, cap=None):
+        """6-connected label pairs and centres (z, y, x) of a device label volume: (edges [cap,2], n_edges dev, cap, centres [nb,3])"""
+        torch, lib = self.torch, self.lib
+        D, H, W = (int(v) for v in d_seg.shape)
+        if cap is None:
+            cap = max(64, 16 * int(nb))
+        wsb = lib.isb_adjacency_workspace_bytes(int(nb), int(cap))
+        ws = self.buf('ws_adj', (wsb,), torch.uint8)
+        edges = self.buf('edges', (cap, 2), torch.int32)
+        n_edges = self.buf('n_edges', (1,), torch.int32)
+        self._ck(lib.isb_adjacency_edges_3d(_lib.ptr(d_seg), D, H, W, int(nb), _lib.ptr(edges), int(cap), _lib.ptr(n_edges), _lib.ptr(ws),
+                                            C.c_size_t(wsb), _lib.stream_ptr()))
+        centres = self.buf('centres3d', (nb, 3), torch.float64)
+        cws = self.buf('ws_centres3d', (4 * int(nb),), torch.int64)
+        self._ck(lib.isb_centroids_3d(_lib.ptr(d_seg), D, H, W, int(nb), _lib.ptr(centres), _lib.ptr(cws), C.c_size_t(32 * int(nb)),
+                                      _lib.stream_ptr()))
+        return edges, n_edges, cap, centres
 
     def slic_label_bound(self, H, W, n_segments, min_size_factor=0.5):
         """upper bound on the number of labels after connectivity enforcement (each kept label has >= min_size px)"""

@@ -367,6 +367,8 @@ def compute_edge_weights(segments, image=None, features=None, proba=None, edge_t
         weights[weights < 1. / MIN_MAX_EDGE_WEIGHT] = 1. / MIN_MAX_EDGE_WEIGHT
         weights[weights > MIN_MAX_EDGE_WEIGHT] = MIN_MAX_EDGE_WEIGHT
         return edges, weights
+    if segments.ndim == 3:
+        return _edge_weights_volume(eng, segments, proba, edge_type)
     mode = _edge_mode(edge_type)
     d_seg, nb, d_edges, E = _device_graph(eng, segments)
     K = 1 if proba is None else int(np.asarray(proba).shape[1])
@@ -380,6 +382,34 @@ def compute_edge_weights(segments, image=None, features=None, proba=None, edge_t
     _, edge_w, _, _, _ = eng.gc_energies(d_proba, d_edges, E, None, centres, mode, 1.0, np.zeros((K, K)))
     edges = eng.to_host(d_edges[:E]).copy() if E else np.zeros((0, 2), dtype=np.int32)
     weights = eng.to_host(edge_w[:E]).copy() if E else np.zeros(0)
+    return edges, weights
+
+
+def _edge_weights_volume(eng, segments, proba, edge_type):
+    """edges and weights of a label VOLUME: the 6-connected pairs and the centres come from the device (isb_adjacency_edges_3d,
+    isb_centroids_3d), the per-edge arithmetic -- a few thousand edges -- follows the reference on the host (graph_cuts.py:617-657)"""
+    _edge_mode(edge_type)     # validates the name
+    nb = int(segments.max()) + 1
+    d_seg = eng.to_device(segments.astype(np.int32, copy=False), 'seg_in3d')
+    cap = None
+    while True:
+        d_edges, d_n, cap, d_centres = eng.graph3d(d_seg, nb, cap)
+        E = int(eng.to_host(d_n)[0])
+        if E <= cap:
+            break
+        cap = 2 * E
+    edges = eng.to_host(d_edges[:E]).copy() if E else np.zeros((0, 2), dtype=np.int32)
+    if not E:
+        return edges, np.zeros(0)
+    if edge_type.startswith('model'):
+        metric = edge_type.split('_')[-1] if '_' in edge_type else 'lT'
+        weights = np.array(compute_edge_model(edges, proba, metric), dtype=float)
+    else:
+        weights = np.ones(len(edges))
+    if edge_type in ('model', 'spatial'):
+        weights = weights / compute_spatial_dist(eng.to_host(d_centres).copy(), edges, relative=True)
+    weights[weights < 1. / MIN_MAX_EDGE_WEIGHT] = 1. / MIN_MAX_EDGE_WEIGHT
+    weights[weights > MIN_MAX_EDGE_WEIGHT] = MIN_MAX_EDGE_WEIGHT
     return edges, weights
 
 
@@ -405,7 +435,7 @@ def segment_graph_cut_general(segments, proba, image=None, features=None, gc_reg
             insert_gc_debug_images(debug_visual, segments, graph_labels, unary_cost, edges, edge_weights * edge_cost)
         return graph_labels
     eng = get_engine()
-    if edge_type in ('color', 'features'):
+    if edge_type in ('color', 'features') or segments.ndim == 3:
         edges, edge_weights = compute_edge_weights(segments, image, features, proba, edge_type)
         edge_weights = edge_weights * edge_cost
         unary_cost = compute_unary_cost(proba)

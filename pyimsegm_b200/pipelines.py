@@ -340,10 +340,24 @@ def train_classif_color2d_slic_features(list_images, list_annots, dict_features,
 
 def pipe_gray3d_slic_features_model_graphcut(image, nb_classes, dict_features, spacing=(12, 1, 1), sp_size=15, sp_regul=0.2,
                                              gc_regul=0.1):
-    """ the gray-volume variant of the pipeline (reference pipelines.py:382-431): needs the 3-D SLIC of
-    ``superpixels.segment_slic_img3d_gray``, which is not part of the accelerated hot path yet (SURVEY.md section 8f, rank 3);
-    the gray-volume statistics (``descriptors.compute_selected_features_gray3d``) and the graph cut are """
-    raise NotImplementedError('3-D gray SLIC is outside the B200 hot path (SURVEY.md section 8f, rank 3)')
+    """ the pipeline for a gray VOLUME: 3-D SLIC supervoxels, their features, a class model, GraphCut over the 6-connected
+    supervoxel graph (reference pipelines.py:382-431)
+
+    :param ndarray image: gray volume [D, H, W]
+    :param tuple(int,int,int) spacing: voxel spacing (z, y, x)
+    :return ndarray: class per voxel [D, H, W]
+    """
+    from .descriptors import compute_selected_features_gray3d, norm_features
+    from .superpixels import segment_slic_img3d_gray
+    image = np.asarray(image)
+    slic = segment_slic_img3d_gray(image, sp_size=sp_size, relative_compact=sp_regul, space=spacing)
+    features, _ = compute_selected_features_gray3d(image, slic, dict_features)
+    features[np.isnan(features)] = 0
+    features, _ = norm_features(features)
+    model = estim_class_model(features, nb_classes)
+    proba = model.predict_proba(features)
+    graph_labels = segment_graph_cut_general(slic, proba, image, features, gc_regul)
+    return graph_labels[slic]
 
 
 def segment_resident(d_image, model, dict_features, sp_size=30, sp_regul=0.2, gc_regul=1., gc_edge_type='model'):

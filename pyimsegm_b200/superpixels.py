@@ -64,8 +64,32 @@ def segment_slic_img2d(img, sp_size=50, relative_compact=0.1, slico=False):
 
 
 def segment_slic_img3d_gray(im, sp_size=50, relative_compact=0.1, space=IMAGE_SPACING):
-    """3-D gray SLIC (reference superpixels.py:72-112) -- not part of the accelerated hot path yet"""
-    raise NotImplementedError('3-D gray SLIC is outside the B200 hot path (SURVEY.md section 8f, rank 3)')
+    """ SLIC superpixels of a gray volume with anisotropic voxel spacing, computed on the GPU (reference superpixels.py:72-112)
+
+    :param ndarray im: input volume [D, H, W]
+    :param int sp_size: superpixel initial size
+    :param float relative_compact: relative regularisation in range (0, 1)
+    :param tuple(int,int,int) space: voxel spacing (z, y, x)
+    :return ndarray: labels [D, H, W], int64
+
+    The reference closes with ``skimage.measure.label`` (:111): with full connectivity and background 0 it renumbers the labels in
+    the order of their first voxel and leaves label 0 alone -- the order the connectivity pass has already produced, so the map
+    is returned as it is (oracle/__init__.py ``segment_slic_img3d_gray``, tests/test_oracle_goldens.py).
+    """
+    im = np.asarray(im)
+    if im.ndim != 3:
+        raise ValueError('expected a gray volume [D, H, W], got shape %r' % (im.shape, ))
+    nb_pixels = np.prod(im.shape)
+    size = np.prod(sp_size / np.asarray(space, dtype=np.float32) * min(space))
+    n_seg = int(nb_pixels / size)
+    compact = int((size * relative_compact) ** 1.5)
+    logging.debug('SLIC 3d gray: NB=%i compact=%f spacing=%r volume %r', n_seg, compact, space, im.shape)
+    if n_seg < 1 or compact < 1:
+        raise ValueError('superpixel size %r / compactness do not fit the volume %r' % (sp_size, im.shape))
+    eng = get_engine()
+    d_vol = eng.to_device(_supported_dtype(im), 'volume')
+    labels, _ = eng.slic3d(d_vol, n_seg, compact, space, sigma=1.0)
+    return eng.to_host(labels).astype(np.int64)
 
 
 def make_graph_segment_connect_edges(vertices, all_edges):
