@@ -28,3 +28,14 @@ print('banded pipe ok', s2.shape, rows, bool(np.array_equal(s2, pl.pipe_color2d_
 X = np.concatenate([c + rng.normal(0, 0.5, (120, 24)) for c in rng.normal(0, 2.0, (3, 24))])
 m = gc.estim_class_model(X, 3)
 print('large-D gmm ok', np.bincount(m.predict_proba(X).argmax(1)))
+# gray-volume path and the descriptor drivers
+from pyimsegm_b200 import descriptors as ds, superpixels as sp
+vol = rng.random_sample((6, 40, 44))
+vol[:, :, 22:] += 1.0
+sv = sp.segment_slic_img3d_gray(vol, 8, 0.3, (2, 1, 1))
+print('volume slic ok', sv.max() + 1)
+print('volume pipe ok', np.bincount(pl.pipe_gray3d_slic_features_model_graphcut(vol, 2, {'color': ['mean', 'std']}, spacing=(2, 1, 1), sp_size=8).ravel()))
+print('volume texture ok', ds.compute_texture_desc_lm_img3d_val(vol[:2, :20, :24], sv[:2, :20, :24], ('mean', 'energy'), 'short')[0].shape)
+pts = [(0, 0), (95, 135), (40, 60)]
+print('hist ok', ds.compute_label_histograms_positions(segm, pts, [2, 5, 9])[0].shape, ds.compute_label_hist_segm(segm, (3, 4), np.ones((7, 5)), 3)[1])
+print('ray ok', ds.compute_ray_features_positions(segm, pts, 30, border_labels=[0])[0].shape)
