@@ -116,6 +116,9 @@ def _argmin_labels_device(eng, proba):
     return eng.to_device(graph_labels, 'gc_labels_in')
 
 
+#: start the download of segm_soft (it only needs the class probabilities) on a side stream while the graph is cut
+EARLY_SOFT_DOWNLOAD = True
+
 #: initial capacity of the device edge table, in edges per (upper bound of) superpixel; grown x4 on overflow
 EDGE_CAP_PER_NODE = [8]
 
@@ -211,8 +214,14 @@ def _segment(image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_t
     while True:
         early.clear()
         d_segm, d_soft, check = _run_resident(eng, image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type,
-                                              soft_sink=soft_sink)
-        if check is None:   # no graph cut: both gathers were done at the end of the main stream
+                                              soft_sink=soft_sink if EARLY_SOFT_DOWNLOAD else None)
+        if check is None or not early:   # no graph cut / overlap switched off: both gathers were done at the end of the main stream
+            if check is not None:
+                segm, soft, n_edges = _download_results(eng, (d_segm, d_soft, check[0]))
+                if int(n_edges[0]) <= check[1]:
+                    break
+                EDGE_CAP_PER_NODE[0] *= 4
+                continue
             segm, soft = _download_results(eng, (d_segm, d_soft))
             break
         segm, n_edges = _download_results(eng, (d_segm, check[0]))
