@@ -322,6 +322,15 @@ def run_ours(args):
         line['cpu_baseline'] = {'value': v, 'unit': 'MPix/s', 'cores': 1, 'kind': 'port',
                                 'sample': '%d image(s) of 2048x2048, single thread (the reference is single-threaded per image), %.1f s' % (args.cpu_images, dt),
                                 'host_cpus': os.cpu_count()}
+        # the CPU leg doubles as the parity gate of SURVEY.md section 8(d): the first sample image through both paths
+        import oracle
+        img0 = synth_image(1000)
+        o_slic, o_fts = oracle.compute_color2d_superpixels_features(img0, ('mean',), SP_SIZE, SP_REGUL)
+        d_slic, d_fts = pipelines.compute_color2d_superpixels_features(img0, FEATURES, sp_size=SP_SIZE, sp_regul=SP_REGUL)
+        same = bool(np.array_equal(o_slic, d_slic))
+        line['parity'] = {'image': 'synth_image(1000), 2048x2048', 'superpixel_label_map_identical': same,
+                          'nb_superpixels': int(d_slic.max()) + 1,
+                          'features_max_abs_err': float(np.max(np.abs(o_fts - d_fts))) if same and o_fts.shape == d_fts.shape else None}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

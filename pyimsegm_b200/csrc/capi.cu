@@ -15,7 +15,7 @@ void isb_set_error(const char* fmt, ...)
 }
 
 extern "C" const char* isb_last_error(void) { return g_err; }
-extern "C" int isb_abi_version(void) { return 2; }
+extern "C" int isb_abi_version(void) { return 3; }  // 3: row bands, large-D class model, volume path, descriptor drivers
 extern "C" long long isb_launch_count(void) { return g_isb_launches; }
 
 // ---- stage timers: CUDA events recorded on the launching stream around a kernel (or a family of kernels) ----

@@ -93,10 +93,6 @@ def default_comm(group=None):
     return LoopbackComm()
 
 
-class HaloError(RuntimeError):
-    """a pixel kept the label of a cluster whose centre is further than the halo away (an orphan no window covers)"""
-
-
 class TiledSuperpixels(object):
     """device-resident result of :func:`slic_tiled`"""
     shape = bands = local = d_raw = d_seg = d_n_labels = nb_bound = d_feat = d_centres = d_err = None
