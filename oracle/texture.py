@@ -6,8 +6,9 @@ texture descriptors:
     imsegm/descriptors.py:880-948   make_gaussian_filter1d / make_edge_filter2d / create_filter_bank_lm_2d
     imsegm/descriptors.py:951-980   compute_img_filter_response2d / 3d  (ndimage.convolve, max over orientations)
     imsegm/descriptors.py:1041-1106 compute_texture_desc_lm_img2d_clr   (sigma-150 background, clip 1e6, log-norm, statistics)
-Pinned by the reference only through SHAPES and NAMES (descriptors.py:911-922, 1052-1074, 1235-1239); the arithmetic is
-SciPy's, which is installed, so the restatement is mechanically checkable.
+The reference's doctests pin only SHAPES and NAMES (descriptors.py:911-922, 1052-1074, 1235-1239), but its own functions run in
+this container (tests/golden/make_goldens.py): the bank and the descriptors of a textured image are pinned on their outputs
+(tests/golden/reference_vectors.npz, tests/test_reference_vectors.py).
 """
 import numpy as np
 from scipy import ndimage
