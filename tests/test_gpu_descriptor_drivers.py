@@ -153,4 +153,4 @@ def test_supervised_data_step_labels_follow_the_annotation():
     assert known.mean() > 0.7 and np.array_equal(labels[known], inside[known])
     assert np.all(labels[np.unique(slic[:8])] == -1)          # superpixels inside the unknown strip
     with pytest.raises(NotImplementedError):
-        pl.pipe_gray3d_slic_features_model_graphcut(np.zeros((4, 20, 20)), 2, {'color': ['mean']})
+        pl.train_classif_color2d_slic_features([img], [annot], {'color': ['mean']})
