@@ -133,10 +133,11 @@ def main():
     _, g_edges = sp.make_graph_segm_connect_grid2d_conn4(seg)
     annot = (img[..., 0] > 0.35).astype(int) + (img[..., 1] > 0.6)
     out.update(graph_edges=np.array(g_edges), annot=annot, region_hist_norm=lb.histogram_regions_labels_norm(seg, annot))
-    path = os.path.join(HERE, 'reference_vectors.npz')
-    np.savez_compressed(path, **out)
-    print('wrote %s: %d arrays, %.0f KB' % (path, len(out), os.path.getsize(path) / 1024))
+    return out
 
 
 if __name__ == '__main__':
-    main()
+    vectors = main()
+    path = os.path.join(HERE, 'reference_vectors.npz')
+    np.savez_compressed(path, **vectors)
+    print('wrote %s: %d arrays, %.0f KB' % (path, len(vectors), os.path.getsize(path) / 1024))

@@ -109,3 +109,34 @@ def test_device_matches_the_reference_outputs(ref):
     # graph and region / annotation histogram
     assert sorted(map(tuple, np.asarray(sp.make_graph_segm_connect_grid2d_conn4(seg)[1]).tolist())) == sorted(map(tuple, ref['graph_edges'].tolist()))
     np.testing.assert_allclose(lb.histogram_regions_labels_norm(seg, ref['annot']), ref['region_hist_norm'], rtol=1e-12)
+
+
+def test_fixture_is_reproducible_from_the_reference(ref):
+    """where the reference tree is present (this container, not the GPU box) the generator must reproduce the committed fixture"""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    if not os.path.isdir('/root/reference/imsegm'):
+        pytest.skip('/root/reference is not present here')
+    code = ('import sys, numpy as np; sys.path.insert(0, %r); import make_goldens as m; v = m.main(); '
+            'g = np.load(%r); assert sorted(v) == sorted(g.files), "array names differ"; '
+            'bad = [k for k in g.files if not (np.array_equal(np.asarray(v[k]), g[k]) or (np.asarray(v[k]).dtype.kind == "f" and '
+            'np.allclose(np.asarray(v[k]), g[k], rtol=0, atol=0, equal_nan=True)))]; assert not bad, bad; print("REPRODUCED", len(g.files))'
+            % (os.path.join(here, 'golden'), GOLD))
+    out = subprocess.run([sys.executable, '-c', code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    text = out.stdout.decode(errors='replace')
+    assert out.returncode == 0 and 'REPRODUCED' in text, text[-2000:]
+
+
+def test_volume_connectivity_oracle_reduces_to_the_2d_one(oracle):
+    """oracle_enforce_connectivity3d on a one-slice volume is the 2-D pass (its z neighbours never exist)"""
+    import ctypes as C
+    rng = np.random.RandomState(11)
+    seg = rng.randint(0, 6, (40, 52)).astype(np.int64)
+    seg[10:30, 5:25] = 7
+    for min_size, max_size in ((2, 30), (6, 400), (1, 3)):
+        want = oracle.enforce_connectivity(seg, min_size, max_size)
+        got = np.empty_like(seg)
+        oracle.lib().oracle_enforce_connectivity3d(seg.ctypes.data_as(C.POINTER(C.c_int64)), 1, 40, 52, C.c_long(min_size), C.c_long(max_size),
+                                                   got.ctypes.data_as(C.POINTER(C.c_int64)))
+        assert np.array_equal(got, want), (min_size, max_size)
