@@ -267,20 +267,26 @@ int isb_gmm_fit_predict(const double* feat, int N, int D, int ld, const int32_t*
                         double* params_out, void* ws, size_t ws_bytes, isb_stream_t stream);
 
 /* compute_texture_desc_lm_img2d_clr (imsegm/descriptors.py:1041-1106): sigma-150 background subtraction (reflect, all three
- * axes), Leung-Malik filter bank (33x33 kernels) as an implicit GEMM on the tensor cores (3xTF32, FP32 accumulate), max over
- * the orientations of a battery, clip at 1e6, log-norm scaling, per-superpixel mean / std / energy -- responses never leave
- * the SM.
+ * axes), Leung-Malik filter bank (33x33 kernels) as an implicit GEMM on the tensor cores (tcgen05.mma kind::tf32 with the 3xTF32
+ * split, FP32 accumulators in tensor memory, operands staged by TMA), max over the orientations of a battery, clip at 1e6,
+ * log-norm scaling, per-superpixel mean / std / energy -- the responses never leave the SM.
  *   bg_weights : device, 2*bg_radius+1 doubles (scipy's gaussian kernel, sigma 150 -> radius 600); bg_radius 0 = no background
  *   chmix_host : HOST, 3x3 doubles: the same kernel folded onto the reflected length-3 channel axis
- *   w_hi, w_lo : device [33][40][NP] f32: correlation-form (flipped) kernels, tf32-rounded value and tf32-rounded remainder,
- *                taps 33..39 and padding filters zero.  Column order: oriented batteries first (8 filters per n-tile for the
- *                full bank: edge s0 | bar s0 | edge s1 | ...; 4+4 per tile for the short bank), then gauss/LoG/LoG2 per sigma
- *   (orient, NP, n_batt) = (8, 80, 20) full bank | (4, 40, 15) short bank;  flags as isb_segment_stats_2d
+ *   w_tc       : device f32 [33 kernel rows][hi | lo][10 k-chunks][NP/8][8 filters][4 taps]: correlation-form (flipped) kernels in
+ *                the operand layout of the contraction (K-major 8 x 16-byte core matrices), tf32-rounded value and tf32-rounded
+ *                remainder, taps 33..39 and padding filters zero.  Filter (column) order: oriented batteries first (edge s0 |
+ *                bar s0 | edge s1 | ..., `orient` filters each), then gauss / LoG / LoG2 per sigma
+ *   (orient, NP, n_batt) = (8, 80, 20) full bank | (4, 48, 15) short bank;  flags as isb_segment_stats_2d
  *   feat       : out [nb, ld]: columns col0 + battery*3*nflags + stat*3 + channel (the reference's order) */
 size_t isb_lm_workspace_bytes(int H, int W, int nb, int n_batt);
 int isb_lm_texture(const void* img, int dtype, const int32_t* seg, int H, int W, int nb, const double* bg_weights, int bg_radius,
-                   const double* chmix_host, const float* w_hi, const float* w_lo, int NP, int orient, int n_batt, int flags,
+                   const double* chmix_host, const float* w_tc, int NP, int orient, int n_batt, int flags,
                    double* feat, int ld, int col0, void* ws, size_t ws_bytes, isb_stream_t stream);
+
+/* known-answer test of the tensor-core plumbing (tests/test_gpu_umma.py): D[128, N] = A[128, K] * B[N, K]^T with tcgen05.mma
+ * kind::tf32 in one CTA; A, B row-major f32 holding tf32-representable values, N % 16 == 0 (<= 256), K % 8 == 0 (<= 64).
+ * variant 0 = the descriptor convention the library uses; 1 = leading/stride byte offsets swapped (diagnostic only). */
+int isb_umma_selftest(const float* A, const float* B, int N, int K, int variant, float* D, isb_stream_t stream);
 
 /* dst[0..n) = value (initial labeling of isb_alpha_expansion and similar small fills) */
 int isb_fill_i32(int32_t* dst, long long n, int32_t value, isb_stream_t stream);

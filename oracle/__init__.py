@@ -218,6 +218,18 @@ def color2d_std(img, seg, means=None):
     return np.sqrt(color2d_stat(img, seg, 2, means))
 
 
+def color2d_median(img, seg):
+    """imsegm/descriptors.py:420-455 numpy_img2d_color_median: per label and channel, np.median of the member pixels"""
+    img, seg = np.asarray(img, dtype=np.float64), np.asarray(seg)
+    nb = int(seg.max()) + 1
+    out = np.full((nb, 3), np.nan)
+    for lb in range(nb):
+        mask = seg == lb
+        if mask.any():
+            out[lb] = np.median(img[mask], axis=0)
+    return out
+
+
 def image2d_color_statistic(image, segm, flags):
     """imsegm/descriptors.py:787-863 for the natively computed statistics (mean / std / energy / meanGrad)"""
     image = np.nan_to_num(np.asarray(image))
@@ -231,7 +243,7 @@ def image2d_color_statistic(image, segm, flags):
     if 'energy' in flags:
         cols.append(color2d_energy(image, segm))
     if 'median' in flags:
-        raise NotImplementedError('median has no native path in the reference (descriptors.py:420)')
+        cols.append(color2d_median(image, segm))
     if 'meanGrad' in flags:
         grad = np.zeros_like(image, dtype=float)
         for i in range(3):

@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(NT) k_gc_build_csr(GcArgs a)
     __shared__ int s_scan[NT];
     __shared__ int s_carry;
     const int N = a.n_nodes_dev ? min(*a.n_nodes_dev, a.N) : a.N;
-    const int E = a.n_edges_dev ? min(*a.n_edges_dev, a.E_cap) : a.E_cap;
+    // an overflowed edge table (count > capacity) holds unspecified rows: cut nothing, the host sees the count and redoes the image
+    const int E = a.n_edges_dev ? (*a.n_edges_dev > a.E_cap ? 0 : *a.n_edges_dev) : a.E_cap;
     for (int v = threadIdx.x; v < N; v += NT) a.fill[v] = 0;
     __syncthreads();
     for (int e = threadIdx.x; e < E; e += NT) { atomicAdd(&a.fill[a.edges[2 * e]], 1); atomicAdd(&a.fill[a.edges[2 * e + 1]], 1); }
@@ -292,7 +293,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) k_alpha_expa
     c.rank = (int)cl.block_rank();
     c.N = a.n_nodes_dev ? min(*a.n_nodes_dev, a.N) : a.N;
     c.K = a.K;
-    c.E = a.n_edges_dev ? min(*a.n_edges_dev, a.E_cap) : a.E_cap;
+    c.E = a.n_edges_dev ? (*a.n_edges_dev > a.E_cap ? 0 : *a.n_edges_dev) : a.E_cap;
     c.A = 2 * c.E;
     c.edges = a.edges; c.w = a.w; c.D = a.D; c.V = a.V;
     c.s_V = s_V; c.s_red = s_red; c.red = a.red; c.peers = &s_peers;
@@ -562,10 +563,14 @@ extern "C" int isb_alpha_expansion(int N, const int32_t* n_nodes_dev, int K, int
     // whether the flow state fits in the cluster's shared memory or stays in the global workspace
     const size_t smem_max = 227 * 1024 - 8 * 1024; // leave room for the static arrays
     a.dyn_bytes = (int)smem_max;
-    static bool attr_set = false;
-    if (!attr_set) {
-        ISB_CUDA_CHECK(cudaFuncSetAttribute(k_alpha_expansion, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-        attr_set = true;
+    {   // the attribute is per device: set it once for every device this process launches on
+        static bool attr_set[64] = {};
+        int dev = 0;
+        ISB_CUDA_CHECK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            ISB_CUDA_CHECK(cudaFuncSetAttribute(k_alpha_expansion, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
     }
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(ISB_PROF_GC, st);

@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(1024) k_gc_energies(const double* __restrict__
                                                       double* edge_w, int* unary_i, int* edge_wi, int* smooth_i, double* sp)
 {
     __shared__ double s_red[32];
-    const int E = n_edges_dev ? min(*n_edges_dev, E_in) : E_in;
+    // an overflowed edge table (count > capacity) holds unspecified rows: no edge is read, the host redoes the image
+    const int E = n_edges_dev ? (*n_edges_dev > E_in ? 0 : *n_edges_dev) : E_in;
     const int N = n_nodes_dev ? min(*n_nodes_dev, N_in) : N_in;
     // unary = |-log(clip(p, 0.01, 0.99))|
     double umax = 0.0;

@@ -1,0 +1,73 @@
+// umma_selftest.cu -- known-answer test of the tcgen05 plumbing in umma.cuh (descriptor encodings, tensor-memory allocation,
+// commit -> mbarrier, tcgen05.ld lane mapping): D[128, N] = A[128, K] * B[N, K]^T in one CTA with TF32 inputs and an FP32
+// accumulator in tensor memory.  Test infrastructure for tests/test_gpu_umma.py; the Leung-Malik contraction (lm_texture.cu)
+// uses exactly these operand layouts.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+using namespace umma;
+
+// A [128][K] and B [N][K] row-major f32 in global memory (values already representable in tf32), K % 8 == 0, N % 16 == 0
+__global__ void __launch_bounds__(128) k_umma_selftest(const float* __restrict__ A, const float* __restrict__ B, int N, int K, int variant,
+                                                       float* __restrict__ D)
+{
+    extern __shared__ __align__(128) unsigned char sm[];
+    float* sA = (float*)sm;                 // [K/4][16][8][4]
+    float* sB = sA + 128 * K;               // [K/4][N/8][8][4]
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 128 * K; i += 128) {
+        const int m = i / K, k = i - m * K;
+        sA[(k >> 2) * (16 * 32) + (m >> 3) * 32 + (m & 7) * 4 + (k & 3)] = A[i];
+    }
+    for (int i = tid; i < N * K; i += 128) {
+        const int n = i / K, k = i - n * K;
+        sB[(k >> 2) * ((N >> 3) * 32) + (n >> 3) * 32 + (n & 7) * 4 + (k & 3)] = B[i];
+    }
+    if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
+    fence_proxy_async();
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base), 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_base;
+    if (tid == 0) {
+        const uint32_t idesc = instr_desc(FMT_TF32, 128, N);
+        const uint32_t a_lbo = 16 * 128, b_lbo = (uint32_t)(N >> 3) * 128, sbo = 128;
+        for (int kk = 0; kk < K / 8; ++kk) {
+            const uint32_t a_addr = smem_u32(sA) + kk * 2 * a_lbo, b_addr = smem_u32(sB) + kk * 2 * b_lbo;
+            const uint64_t ad = variant ? smem_desc(a_addr, sbo, a_lbo) : smem_desc(a_addr, a_lbo, sbo);
+            const uint64_t bd = variant ? smem_desc(b_addr, sbo, b_lbo) : smem_desc(b_addr, b_lbo, sbo);
+            mma_tf32(tbase, ad, bd, idesc, kk > 0);
+        }
+        tc_commit(smem_u32(&bar));
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    tc_fence_after();
+    const int m = tid; // lane of tensor memory = row of D
+    for (int c = 0; c < N; c += 16) {
+        float v[16];
+        tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + c, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) D[(size_t)m * N + c + j] = v[j];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 128);
+}
+
+} // namespace
+
+extern "C" int isb_umma_selftest(const float* A, const float* B, int N, int K, int variant, float* D, isb_stream_t stream)
+{
+    ISB_REQUIRE(A && B && D, "null pointer");
+    ISB_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 8 && K <= 64 && K % 8 == 0, "N must be a multiple of 16 <= 256, K a multiple of 8 <= 64");
+    const size_t smem = sizeof(float) * (size_t)(128 + N) * K;
+    ISB_CUDA_CHECK(cudaFuncSetAttribute(k_umma_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_umma_selftest<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, N, K, variant, D);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}

@@ -377,16 +377,10 @@ def compute_img_filter_response3d(img, filter_battery):
     return eng.to_host(out).copy()
 
 
-def image_subtract_gauss_smooth(img, sigma):
-    """ subtract from every slice ``img[i]`` its own Gaussian-smoothed copy -- a high-pass per slice (reference
-    descriptors.py:986-1000; scipy's ``gaussian_filter`` semantics, FP64 on the device) """
+def _gauss_smooth_slices(stack, sigma):
+    """scipy ``gaussian_filter(slice, sigma)`` of every 2-D slice of a float64 stack [n, H, W], FP64 on the device"""
     from . import _lib
     from .engine import gaussian_half_kernel
-    if sigma <= 0:
-        return img
-    src, stack = _as_slices(img)
-    if src.ndim != 3:
-        raise ValueError('expected a stack of 2-D slices, got shape %r' % (src.shape, ))
     w_half, radius = gaussian_half_kernel(sigma)
     eng = get_engine()
     d_img = eng.to_device(stack, 'smooth_img')
@@ -395,7 +389,18 @@ def image_subtract_gauss_smooth(img, sigma):
     out = eng.buf('smooth_out', stack.shape, eng.torch.float64)
     _lib.check(eng.lib.isb_gaussian_filter_2d(_lib.ptr(d_img), stack.shape[0], stack.shape[1], stack.shape[2], _lib.ptr(d_w), radius,
                                               _lib.ptr(tmp), _lib.ptr(out), _lib.stream_ptr()))
-    return np.asarray(img) - eng.to_host(out).reshape(src.shape)
+    return eng.to_host(out).copy()
+
+
+def image_subtract_gauss_smooth(img, sigma):
+    """ subtract from every slice ``img[i]`` its own Gaussian-smoothed copy -- a high-pass per slice (reference
+    descriptors.py:986-1000; scipy's ``gaussian_filter`` semantics, FP64 on the device) """
+    if sigma <= 0:
+        return img
+    src, stack = _as_slices(img)
+    if src.ndim != 3:
+        raise ValueError('expected a stack of 2-D slices, got shape %r' % (src.shape, ))
+    return np.asarray(img) - _gauss_smooth_slices(stack, sigma).reshape(src.shape)
 
 
 def compute_texture_desc_lm_img3d_val(img, seg, feature_flags, bank_type='normal'):
@@ -815,9 +820,17 @@ def compute_selected_features_color2d(img, segments, feature_flags=FEATURES_SET_
 
 
 def compute_selected_features_gray2d(img, segments, features_flags=FEATURES_SET_ALL):
-    """gray 2-D features go through the 3-D gray statistics in the reference (descriptors.py:1169-1204);
-    that family is outside the accelerated hot path"""
-    raise NotImplementedError('gray-image descriptors are outside the B200 hot path (SURVEY.md section 8f)')
+    """ selected features of a gray 2-D image: the reference treats it as a one-slice volume
+    (reference descriptors.py:1167-1204; golden values :1179-1197)
+
+    :return tuple(ndarray,list(str)): features [nb_segments, nb_features], names
+    """
+    img, segments = np.asarray(img), np.asarray(segments)
+    _check_gray_image_segm(img, segments)
+    features, names = compute_selected_features_gray3d(img[np.newaxis, ...], segments[np.newaxis, ...], features_flags)
+    if features.shape[1] != len(names):
+        raise ValueError('features: %r and names %r' % (features.shape, names))
+    return features, names
 
 
 def compute_selected_features_img2d(image, segm, features_flags=FEATURES_SET_COLOR):

@@ -78,6 +78,9 @@ class Engine(object):
     def buf(self, name, shape, dtype):
         """cached device buffer (grown on demand, never shrunk)"""
         torch = self.torch
+        if torch.cuda.current_device() != self.device.index:
+            # the C-ABI calls launch on the CURRENT device's stream: an engine must only be driven with its own device current
+            raise RuntimeError('Engine of cuda:%d used while cuda:%d is the current device' % (self.device.index, torch.cuda.current_device()))
         shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
         n = int(np.prod(shape)) if shape else 1
         cur = self._bufs.get(name)

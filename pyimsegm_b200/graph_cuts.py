@@ -32,7 +32,7 @@ USE_DEVICE_GMM = True
 #: seed of the device k-means++ initialisation (the reference leaves its model unseeded)
 RANDOM_SEED = 0
 #: D <= 16 runs as one kernel (a CTA per restart), 16 < D <= 256 (colour + Leung-Malik = 189) as batched FP64 GEMMs
-DEVICE_GMM_MAX_FEATURES, DEVICE_GMM_MAX_CLASSES = 256, 8
+DEVICE_GMM_MAX_FEATURES, DEVICE_GMM_MAX_CLASSES = 232, 8   # = DBIG of csrc/gmm.cu
 
 
 # ---------------------------------------------------------------------------------------------------------------------

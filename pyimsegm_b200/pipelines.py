@@ -283,7 +283,7 @@ def segment_images_batch(list_images, nb_classes=None, dict_features=FTS_SET_SIM
         segm, soft = hosts[0].numpy(), hosts[1].numpy()
         if check is not None and int(hosts[2].numpy()[0]) > check[1]:
             EDGE_CAP_PER_NODE[0] *= 4  # edge table overflow (not seen in practice): redo this image through the single-image path
-            segm, soft = _segment(list_images[idx], model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type, None)
+            segm, soft = _segment(list_images[idx], model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type, None, classes=classes)
         elif classes is not None:
             segm = np.asarray(classes)[segm]
         results[idx] = (segm, soft)

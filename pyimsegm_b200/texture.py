@@ -3,7 +3,7 @@ Leung-Malik texture descriptors on the GPU (reference ``imsegm/descriptors.py:88
 
 Host side: the filter bank is built with numpy/scipy exactly like the reference does at run time
 (``create_filter_bank_lm_2d``, descriptors.py:903-948), then laid out for the tensor-core contraction of
-``isb_lm_texture`` (correlation form, oriented batteries first, tf32 hi/lo split).  The contraction, the battery max,
+``isb_lm_texture`` (correlation form, oriented batteries first, tf32 hi/lo split, operand layout).  The contraction, the battery max,
 the log-norm scaling and the per-superpixel statistics run in CUDA (``csrc/lm_texture.cu``).
 """
 import ctypes as C
@@ -75,7 +75,8 @@ def _round_tf32(x):
 
 
 def _device_bank(bank_type):
-    """(names, d_w_hi, d_w_lo, NP, orient, n_batt) for 'normal' / 'short', cached per device"""
+    """(names, d_w_tc, NP, orient, n_batt) for 'normal' / 'short', cached per device.  ``d_w_tc`` holds, per kernel row, the weights
+    in the operand layout of the tensor-core contraction (see isb_lm_texture): [33][hi|lo][10][NP/8][8][4] float32"""
     eng = get_engine()
     key = (bank_type, eng.device.index)
     if key in _BANK_CACHE:
@@ -83,33 +84,29 @@ def _device_bank(bank_type):
     from .descriptors import SHORT_FILTERS_SIGMAS
     if bank_type == 'short':
         filters, names = create_filter_bank_lm_2d(sigmas=SHORT_FILTERS_SIGMAS, nb_orient=4)
-        orient = 4
+        orient, NP = 4, 48
     else:
         filters, names = create_filter_bank_lm_2d()
-        orient = 8
+        orient, NP = 8, 80
     n_sig = len(filters) // 5
     cols = []
-    if orient == 8:   # one n-tile per oriented battery: edge s0 | bar s0 | edge s1 | ...
-        for s in range(n_sig):
-            cols += list(filters[5 * s]) + list(filters[5 * s + 1])
-    else:             # 4 + 4 per n-tile: edge then bar of one sigma
-        for s in range(n_sig):
-            cols += list(filters[5 * s]) + list(filters[5 * s + 1])
-    n_oriented = len(cols)
-    for s in range(n_sig):
+    for s in range(n_sig):      # oriented batteries first: edge s0 | bar s0 | edge s1 | ...
+        cols += list(filters[5 * s]) + list(filters[5 * s + 1])
+    for s in range(n_sig):      # then Gauss, LoG(sigma), LoG(sigma^2) per sigma
         cols += [filters[5 * s + 2][0], filters[5 * s + 3][0], filters[5 * s + 4][0]]
-    n_single_pad = -(-(len(cols) - n_oriented) // 8) * 8
-    NP = n_oriented + n_single_pad
+    assert len(cols) <= NP
     w = np.zeros((_KW, _KWP, NP), dtype=np.float64)
     for j, f in enumerate(cols):
         w[:, :_KW, j] = f[::-1, ::-1]          # ndimage.convolve == correlation with the flipped kernel
     w32 = w.astype(np.float32)
     hi = _round_tf32(w32)
     lo = _round_tf32((w32 - hi).astype(np.float32))
+    # [dy][dx][n] -> [dy][half][dx // 4][n // 8][n % 8][dx % 4]: K-major core matrices of 8 filters x 4 taps (16 bytes)
+    both = np.stack([hi, lo], axis=1).reshape(_KW, 2, _KWP // 4, 4, NP // 8, 8)
+    w_tc = np.ascontiguousarray(both.transpose(0, 1, 2, 4, 5, 3))
     torch = eng.torch
-    d_hi = torch.from_numpy(np.ascontiguousarray(hi)).to(eng.device)
-    d_lo = torch.from_numpy(np.ascontiguousarray(lo)).to(eng.device)
-    _BANK_CACHE[key] = (names, d_hi, d_lo, NP, orient, len(filters))
+    d_w = torch.from_numpy(w_tc).to(eng.device)
+    _BANK_CACHE[key] = (names, d_w, NP, orient, len(filters))
     return _BANK_CACHE[key]
 
 
@@ -131,7 +128,7 @@ def background_kernel(sigma=BACKGROUND_SIGMA, truncate=4.0):
 def device_lm_features(eng, d_img, d_seg, nb, flags, bank_type='normal', feat=None, col0=0):
     """run isb_lm_texture on device buffers; returns (feat tensor [nb, ld], names, n_cols)"""
     torch, lib = eng.torch, eng.lib
-    names, d_hi, d_lo, NP, orient, n_batt = _device_bank(bank_type)
+    names, d_w, NP, orient, n_batt = _device_bank(bank_type)
     bits = 0
     for f in flags:
         bits |= FLAG_BITS[f]
@@ -145,9 +142,45 @@ def device_lm_features(eng, d_img, d_seg, nb, flags, bank_type='normal', feat=No
     ws = eng.buf('ws_lm', (wsb,), torch.uint8)
     code = _lib.DTYPE_CODES[str(d_img.dtype).replace('torch.', '')]
     _lib.check(lib.isb_lm_texture(_lib.ptr(d_img), code, _lib.ptr(d_seg), H, W, int(nb), _lib.ptr(d_wbg), radius,
-                                  mix.ctypes.data_as(C.POINTER(C.c_double)), _lib.ptr(d_hi), _lib.ptr(d_lo), NP, orient, n_batt, bits,
+                                  mix.ctypes.data_as(C.POINTER(C.c_double)), _lib.ptr(d_w), NP, orient, n_batt, bits,
                                   _lib.ptr(feat), int(feat.shape[1]), int(col0), _lib.ptr(ws), C.c_size_t(wsb), _lib.stream_ptr()))
     return feat, names, ncol
+
+
+def _texture_desc_lm_materialised(img, seg, feature_flags, bank_type):
+    """ the reference's own sequence (descriptors.py:1078-1098) with every array in memory: background (sigma 150 on all three
+    axes), per battery the strongest response per channel (FP64 on the device, ``isb_filter_response_2d``), clip, log-norm
+    scaling, then :func:`compute_image2d_color_statistic` -- the route for the statistics the fused kernel does not produce
+    (``median``, ``meanGrad``) """
+    from .descriptors import (MAX_SIGNAL_RESPONSE, SHORT_FILTERS_SIGMAS, _gauss_smooth_slices, compute_image2d_color_statistic,
+                              compute_img_filter_response3d)
+    img = np.asarray(img, dtype=np.float64)
+    _, _, mix = background_kernel()
+    roll = np.ascontiguousarray(np.rollaxis(img, -1, 0))
+    smooth = _gauss_smooth_slices(roll, BACKGROUND_SIGMA)          # the two image axes ...
+    roll = roll - np.tensordot(mix, smooth, axes=(1, 0))           # ... and the reflected length-3 channel axis
+    if bank_type == 'short':
+        filters, fl_names = create_filter_bank_lm_2d(sigmas=SHORT_FILTERS_SIGMAS, nb_orient=4)
+    else:
+        filters, fl_names = create_filter_bank_lm_2d()
+    features, names = [], []
+    for battery, fl_name in zip(filters, fl_names):
+        resp = compute_img_filter_response3d(roll, battery)
+        resp[resp > MAX_SIGNAL_RESPONSE] = MAX_SIGNAL_RESPONSE
+        norm = np.sqrt(np.sum(resp ** 2))
+        if norm == 0 or abs(norm) == np.inf:
+            resp = np.zeros(resp.shape)
+        else:
+            resp = (resp * (np.log(1 + norm) / 0.03)) / norm
+        fts, ns = compute_image2d_color_statistic(np.rollaxis(resp, 0, 3), seg, feature_flags, fl_name)
+        features.append(fts)
+        names += ns
+    features = np.nan_to_num(np.concatenate(tuple(features), axis=1))
+    features[features == 0] = 0
+    names = ['tLM_%s' % n for n in names]
+    if features.shape[1] != len(names):
+        raise ValueError('features: %r and names %r' % (features.shape, names))
+    return features, names
 
 
 def compute_texture_desc_lm_img2d_clr(img, seg, feature_flags, bank_type='normal'):
@@ -164,10 +197,9 @@ def compute_texture_desc_lm_img2d_clr(img, seg, feature_flags, bank_type='normal
     img, seg = _device_dtype(img), np.asarray(seg)
     _check_color_image(img)
     _check_color_image_segm(img, seg)
-    unsupported = [f for f in feature_flags if f in ('median', 'meanGrad')]
-    if unsupported:
-        raise NotImplementedError('tLM statistics %r need the filter responses in memory; the fused device path computes mean/std/energy'
-                                  % unsupported)
+    if any(f in ('median', 'meanGrad') for f in feature_flags):
+        # these two statistics need the filter responses in memory: per-battery path, exactly the reference's sequence
+        return _texture_desc_lm_materialised(img, seg, feature_flags, bank_type)
     flags = [f for f in ('mean', 'std', 'energy') if f in feature_flags]
     _check_unrecognised_feature_names(feature_flags)
     eng = get_engine()

@@ -233,3 +233,13 @@ def test_host_side_descriptor_helpers_reference_doctests():
     np.testing.assert_allclose(ds.numpy_img3d_gray_std(img, seg)[[0, 1, 2, 5]], [0., 0.5, 0., 0.])
     np.testing.assert_allclose(ds.numpy_img3d_gray_energy(img, seg)[[0, 1, 2, 5]], [0., 0.5, 1., 4.])
     np.testing.assert_allclose(ds.numpy_img3d_gray_median(img, seg)[[0, 1, 2, 5]], [0., 0.5, 1., 2.])
+
+
+def test_color_median_reference_doctest(oracle):
+    """imsegm/descriptors.py:429-437 numpy_img2d_color_median"""
+    image = np.zeros((2, 10, 3))
+    image[:, 2:6, 0] = 1
+    image[:, 3:8, 1] = 3
+    image[:, 4:9, 2] = 2
+    segm = np.array([[0, 0, 0, 0, 1, 1, 1, 1, 1, 1]] * 2)
+    np.testing.assert_allclose(oracle.color2d_median(image, segm), [[0.5, 0., 0.], [0., 3., 2.]])
