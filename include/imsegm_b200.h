@@ -35,6 +35,9 @@ const char* isb_last_error(void);
 int isb_abi_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long long isb_launch_count(void);
+/* a caller that replays a captured CUDA graph of this library's kernels reports the kernels of one replay here, so that
+ * isb_launch_count() keeps counting kernels, not graph launches */
+int isb_note_graph_replay(long long n_kernels);
 /* per-stage device timers: CUDA events recorded on the launching stream around each stage's kernels while enabled.
  * isb_profile_collect() synchronises the recorded events and returns, per stage id, the summed milliseconds and
  * the number of timed launches (arrays of isb_profile_stage_count() entries); it clears the record list. */

@@ -35,6 +35,7 @@ SIGNATURES = {
     'isb_last_error': (C.c_char_p, []),
     'isb_abi_version': (_i, []),
     'isb_launch_count': (_ll, []),
+    'isb_note_graph_replay': (_i, [_ll]),
     'isb_profile_enable': (_i, [_i]),
     'isb_profile_stage_count': (_i, []),
     'isb_profile_stage_name': (C.c_char_p, [_i]),

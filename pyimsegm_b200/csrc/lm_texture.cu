@@ -478,21 +478,6 @@ static size_t carve_lm(LmWs& w, void* ws, size_t bytes, int H, int W, int nb, in
     return isb_align(c.off);
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
 template <int NPAD>
 static int launch_lm_conv(const CUtensorMap& tmap, const LmTcArgs& a, int n_tiles, cudaStream_t st)
 {
@@ -556,7 +541,7 @@ extern "C" int isb_lm_texture(const void* img, int dtype, const int32_t* seg, in
     const LmDims d = lm_dims(H, W);
     k_lm_pad_split<<<dim3((d.Wp + 255) / 256, d.Hp, 3), 256, 0, st>>>(w.imgf, H, W, d.Hp, d.Wp, w.planes);
     ISB_LAUNCH_CHECK();
-    EncodeTiledFn encode = encode_tiled_fn();
+    umma::EncodeTiledFn encode = umma::encode_tiled_fn();
     if (!encode) { isb_set_error("cuTensorMapEncodeTiled is not available from this driver"); return ISB_ERR_UNSUPPORTED; }
     CUtensorMap tmap;
     {

@@ -18,7 +18,9 @@
 // Per sweep HBM traffic (algorithmic): read Lab 24 B/px + write label 4 B/px (assign); the update re-reads
 // labels and member colours through L2.
 #include "common.cuh"
+#include "umma.cuh"
 #include <float.h>
+#include <string.h>
 
 namespace {
 
@@ -160,14 +162,16 @@ __device__ __forceinline__ unsigned long long dbits(double v) { return (unsigned
 // The tile's Lab values are staged in shared memory, candidates are visited nearest-first and the loop stops as soon as
 // the spatial lower bound of every remaining candidate exceeds the worst of the thread's current minima.
 template <bool SLICO>
-__global__ void __launch_bounds__(ATHREADS, 5) k_assign(KmState s, const double* __restrict__ lab, int* __restrict__ labels)
+__global__ void __launch_bounds__(ATHREADS, 5) k_assign(const __grid_constant__ CUtensorMap lab_map, int use_tma, KmState s,
+                                                        const double* __restrict__ lab, int* __restrict__ labels)
 {
     __shared__ Cand cand[ACAP];
     __shared__ double s_maxdc[SLICO ? ACAP : 1];
     __shared__ float s_key[ACAP];
     __shared__ double s_lb[ACAP];          // lower bound of the spatial term of the candidate at sorted position i, and of all later ones
     __shared__ unsigned char s_order[ACAP];
-    __shared__ double s_px[3][TILE][TILE]; // Lab of the tile
+    __shared__ __align__(128) double s_px[3][TILE][TILE]; // Lab of the tile
+    __shared__ __align__(8) unsigned long long s_bar;     // mbarrier of the TMA tile load
     __shared__ int s_ncand, s_done, s_row, s_off, s_total;
     const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
     const int tx1 = min(tx0 + TILE, s.W);
@@ -180,12 +184,22 @@ __global__ void __launch_bounds__(ATHREADS, 5) k_assign(KmState s, const double*
 
     double best[AROWS];
     int bestk[AROWS];
-    {
+#pragma unroll
+    for (int j = 0; j < AROWS; ++j) { best[j] = DBL_MAX; bestk[j] = -1; }
+    if (use_tma) {
+        // the three Lab planes of the tile arrive as ONE 3-D tensor-map load (32 x 32 x 3 doubles, out-of-image elements read as 0)
+        // while every warp gathers the candidate clusters; the distance loop waits on the mbarrier
+        if (threadIdx.x == 0) {
+            umma::mbar_init(umma::smem_u32(&s_bar), 1);
+            umma::fence_mbar_init();
+            umma::mbar_arrive_expect_tx(umma::smem_u32(&s_bar), 3 * TILE * TILE * 8);
+            umma::tma_load_3d(umma::smem_u32(&s_px[0][0][0]), &lab_map, tx0, ty0, 0, umma::smem_u32(&s_bar));
+        }
+    } else {
         double v[3][AROWS];
 #pragma unroll
         for (int j = 0; j < AROWS; ++j) {
             const int y = yb + j;
-            best[j] = DBL_MAX; bestk[j] = -1;
             if (xin && y < s.H) {
                 const size_t p = (size_t)y * s.W + x;
                 v[0][j] = lab[p]; v[1][j] = lab[HW + p]; v[2][j] = lab[2 * HW + p];
@@ -282,6 +296,7 @@ __global__ void __launch_bounds__(ATHREADS, 5) k_assign(KmState s, const double*
             s_lb[rank] = r > 0.f ? (double)(r * r * 0.999f) * s.sw * 0.999 : 0.0;
         }
         __syncthreads();
+        if (use_tma) umma::mbar_wait(umma::smem_u32(&s_bar), 0);   // phase 0 completes once; later rounds pass immediately
         if (xin) {
             const double xd = (double)x;
             unsigned long long worst = dbits(DBL_MAX); // max over the rows of the current minima (bit pattern)
@@ -292,7 +307,8 @@ __global__ void __launch_bounds__(ATHREADS, 5) k_assign(KmState s, const double*
                 const int c = s_order[ci];
                 const int cx0 = cand[c].x0, cx1 = cand[c].x1;
                 if (x < cx0 || x >= cx1) continue;
-                const int cy0 = cand[c].y0, cy1 = cand[c].y1, ck = cand[c].k;
+                const int cy0 = cand[c].y0, ck = cand[c].k;
+                const unsigned cyn = (unsigned)(cand[c].y1 - cy0);   // rows [cy0, cy0 + cyn) are inside the window
                 const double ccy = cand[c].cy;
                 const double tx = __dsub_rn(cand[c].cx, xd);
                 const double dx2 = __dmul_rn(tx, tx);
@@ -300,11 +316,14 @@ __global__ void __launch_bounds__(ATHREADS, 5) k_assign(KmState s, const double*
 #pragma unroll
                 for (int j = 0; j < AROWS; ++j) {
                     const int y = yb + j + s.y_off;
-                    if (y < cy0 || y >= cy1) continue;
-                    const double ty = __dsub_rn(ccy, (double)y);
+                    if ((unsigned)(y - cy0) >= cyn) continue;
+                    // (double)y without the conversion unit: y < 2^31 sits in the low mantissa word of 2^52 + y (exact)
+                    const double yd = __dsub_rn(__hiloint2double(0x43300000, y), 4503599627370496.0);
+                    const double ty = __dsub_rn(ccy, yd);
                     const double sp = __dmul_rn(__dadd_rn(__dmul_rn(ty, ty), dx2), s.sw);
-                    // exact pruning: the colour term is >= 0 and fl(a + b) >= a for b >= 0, so d >= sp > best cannot win or tie
-                    if (dbits(sp) > dbits(best[j])) continue;
+                    // exact pruning: the colour term is >= 0 and fl(a + b) >= a for b >= 0, so d >= sp > best cannot win or tie.
+                    // (a NaN sp falls through: its NaN distance below never compares less than a minimum)
+                    if (sp > best[j]) continue;
                     const int ry = warp * AROWS + j;
                     const double d0 = __dsub_rn(s_px[0][ry][lane], cand[c].c0), d1 = __dsub_rn(s_px[1][ry][lane], cand[c].c1),
                                  d2 = __dsub_rn(s_px[2][ry][lane], cand[c].c2);
@@ -312,8 +331,8 @@ __global__ void __launch_bounds__(ATHREADS, 5) k_assign(KmState s, const double*
                     dcol = __dadd_rn(dcol, __dmul_rn(d1, d1));
                     dcol = __dadd_rn(dcol, __dmul_rn(d2, d2));
                     const double dc = __dadd_rn(sp, SLICO ? __ddiv_rn(dcol, s_maxdc[c]) : dcol);
-                    const unsigned long long bd = dbits(dc), bb = dbits(best[j]);
-                    if (bd < bb || (bd == bb && bestk[j] >= 0 && ck < bestk[j])) { best[j] = dc; bestk[j] = ck; improved = true; }
+                    // distances are >= +0 or NaN: the floating-point order is the order of the bit patterns, a NaN never wins
+                    if (dc < best[j] || (dc == best[j] && bestk[j] >= 0 && ck < bestk[j])) { best[j] = dc; bestk[j] = ck; improved = true; }
                 }
                 if (improved) {
                     worst = 0;
@@ -357,7 +376,7 @@ template <bool BAND>
 __global__ void __launch_bounds__(256) k_update(KmState s, const double* __restrict__ lab, const int* __restrict__ labels,
                                                 long long* __restrict__ xchg)
 {
-    __shared__ double buf[8][3][64];
+    __shared__ double buf[8][3][72];   // two 32-pixel chunks + the zero padding + one look-ahead group
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int k = blockIdx.x * 8 + wl;
     if (k >= s.n) return;
@@ -431,15 +450,21 @@ __global__ void __launch_bounds__(256) k_update(KmState s, const double* __restr
         }
         cnt += nm;
         sy += (long long)(ya + s.y_off) * nm0 + (long long)(yb + s.y_off) * nm1;
+        // pad the run to a multiple of four with +0.0: x + (+0.0) == x for every x the sum can take (it starts at +0.0 and can
+        // therefore never be -0.0), so the padded adds change nothing and the add loop has no remainder
+        if (lane < 4) { buf[wl][0][nm + lane] = 0.0; buf[wl][1][nm + lane] = 0.0; buf[wl][2][nm + lane] = 0.0; }
         __syncwarp();
         if (lane < 3) {
+            // sequential adds in raster order; the next four operands are loaded while the current four are added (the loads do not
+            // depend on the running sum, only the adds form the chain)
             const double* bsrc = buf[wl][lane];
-            int i = 0;
-            for (; i + 4 <= nm; i += 4) {
-                const double d0 = bsrc[i], d1 = bsrc[i + 1], d2 = bsrc[i + 2], d3 = bsrc[i + 3];
-                acc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc, d0), d1), d2), d3);
+            const int ng = (nm + 3) >> 2;
+            double c0 = bsrc[0], c1 = bsrc[1], c2 = bsrc[2], c3 = bsrc[3];
+            for (int g = 1; g <= ng; ++g) {
+                const double n0 = bsrc[4 * g], n1 = bsrc[4 * g + 1], n2 = bsrc[4 * g + 2], n3 = bsrc[4 * g + 3];   // (one group past the end: inside the buffer)
+                acc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc, c0), c1), c2), c3);
+                c0 = n0; c1 = n1; c2 = n2; c3 = n3;
             }
-            for (; i < nm; ++i) acc = __dadd_rn(acc, bsrc[i]);
         }
         __syncwarp();
     }
@@ -565,6 +590,27 @@ static int rebin(KmState& s, const double* seeds_yx, cudaStream_t st)
     return ISB_OK;
 }
 
+// 3-D tensor map over the Lab planes of a slab: (x, y, plane) with a 32 x 32 x 3 box.  TMA needs 16-byte multiples for the row and
+// plane pitches (W and plane stride even) and a 16-byte aligned base; otherwise the kernel stages the tile with ordinary loads.
+static bool make_lab_map(CUtensorMap& map, const double* lab, int rows, int W, size_t plane_stride)
+{
+    umma::EncodeTiledFn encode = umma::encode_tiled_fn();
+    if (!encode || (W & 1) || (plane_stride & 1) || ((uintptr_t)lab & 15)) return false;
+    const cuuint64_t gdim[3] = { (cuuint64_t)W, (cuuint64_t)rows, 3 };
+    const cuuint64_t gstride[2] = { (cuuint64_t)W * sizeof(double), (cuuint64_t)plane_stride * sizeof(double) };
+    const cuuint32_t box[3] = { TILE, TILE, 3 };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    return encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)lab, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static void launch_assign(const KmState& s, const CUtensorMap& map, int use_tma, const double* lab, int* labels, cudaStream_t st)
+{
+    dim3 agrid((s.W + TILE - 1) / TILE, (s.H + TILE - 1) / TILE);
+    if (s.slico) k_assign<true><<<agrid, ATHREADS, 0, st>>>(map, use_tma, s, lab, labels);
+    else k_assign<false><<<agrid, ATHREADS, 0, st>>>(map, use_tma, s, lab, labels);
+}
+
 } // namespace
 
 extern "C" size_t isb_slic_kmeans_workspace_bytes(int H, int W, int n_seeds, int step_y, int step_x)
@@ -587,12 +633,13 @@ extern "C" int isb_slic_kmeans(const double* lab_planar, int H, int W, const dou
     cudaStream_t st = (cudaStream_t)stream;
     ISB_CUDA_CHECK(cudaMemsetAsync(labels, 0, sizeof(int32_t) * (size_t)H * W, st));
     if (int rc = rebin(s, seeds_yx, st)) return rc;
-    dim3 agrid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE);
+    CUtensorMap lab_map;
+    memset(&lab_map, 0, sizeof(lab_map));
+    const int use_tma = make_lab_map(lab_map, lab_planar, H, W, s.pstride) ? 1 : 0;
     for (int it = 0; it < max_iter; ++it) {
         {
             ProfScope p(ISB_PROF_ASSIGN, st);
-            if (slic_zero) k_assign<true><<<agrid, ATHREADS, 0, st>>>(s, lab_planar, labels);
-            else k_assign<false><<<agrid, ATHREADS, 0, st>>>(s, lab_planar, labels);
+            launch_assign(s, lab_map, use_tma, lab_planar, labels, st);
         }
         ISB_LAUNCH_CHECK();
         { ProfScope p(ISB_PROF_UPDATE, st); k_update<false><<<(n_seeds + 7) / 8, 256, 0, st>>>(s, lab_planar, labels, nullptr); }
@@ -654,10 +701,11 @@ extern "C" int isb_slic_band_assign(const isb_slic_band_t* b, isb_stream_t strea
     KmState s;
     if (int rc = band_state(b, s)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 agrid((s.W + TILE - 1) / TILE, (s.H + TILE - 1) / TILE);
+    CUtensorMap lab_map;
+    memset(&lab_map, 0, sizeof(lab_map));
+    const int use_tma = make_lab_map(lab_map, b->lab_slab, s.H, s.W, s.pstride) ? 1 : 0;
     ProfScope p(ISB_PROF_ASSIGN, st);
-    if (s.slico) k_assign<true><<<agrid, ATHREADS, 0, st>>>(s, b->lab_slab, b->labels_slab);
-    else k_assign<false><<<agrid, ATHREADS, 0, st>>>(s, b->lab_slab, b->labels_slab);
+    launch_assign(s, lab_map, use_tma, b->lab_slab, b->labels_slab, st);
     ISB_LAUNCH_CHECK();
     return ISB_OK;
 }

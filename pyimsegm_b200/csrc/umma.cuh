@@ -65,6 +65,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
                  "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst_smem),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
@@ -139,6 +145,22 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+
+// ---------------------------------------------------------------- host: tensor maps ----------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda); nullptr when unavailable
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
 }
 
 } // namespace umma

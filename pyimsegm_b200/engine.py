@@ -89,15 +89,77 @@ class Engine(object):
             self._bufs[name] = cur
         return cur[:n].view(shape)
 
+    #: host arrays at least this large that are NOT page-locked go through the staged upload below
+    STAGE_MIN_BYTES = 4 << 20
+    STAGE_CHUNK = 8 << 20
+    STAGE_SLOTS = 4
+
     def to_device(self, arr, name=None):
-        """host ndarray -> device tensor through the current stream (pinned sources copy asynchronously)"""
+        """host ndarray -> device tensor through the current stream (pinned sources copy asynchronously; large pageable sources
+        are staged, see :meth:`_staged_upload`)"""
         torch = self.torch
         arr = np.ascontiguousarray(arr)
         src = torch.from_numpy(arr)
         if name is None:
             return src.to(self.device, non_blocking=True)
         dst = self.buf(name, arr.shape, src.dtype)
-        dst.copy_(src, non_blocking=True)
+        if arr.nbytes >= self.STAGE_MIN_BYTES and not src.is_pinned():
+            self._staged_upload(dst, arr)
+        else:
+            dst.copy_(src, non_blocking=True)
+        return dst
+
+    def _staged_upload(self, dst, arr):
+        """upload of a large PAGEABLE array (what a caller of the numpy API normally holds): the driver would bounce it through
+        its own small staging buffer at a fraction of the PCIe rate.  Here worker threads copy 8 MB chunks into a ring of pinned
+        buffers (numpy releases the GIL while copying) and every chunk is sent by an asynchronous DMA as soon as it is complete, so
+        the host copies overlap the transfers."""
+        torch = self.torch
+        if getattr(self, '_stage', None) is None:
+            from concurrent.futures import ThreadPoolExecutor
+            slots = [torch.empty(self.STAGE_CHUNK, dtype=torch.uint8, pin_memory=True) for _ in range(self.STAGE_SLOTS)]
+            self._stage = (slots, [t.numpy() for t in slots], [torch.cuda.Event() for _ in slots], [False] * len(slots),
+                           ThreadPoolExecutor(self.STAGE_SLOTS))
+        slots, views, events, used, pool = self._stage
+        src = arr.reshape(-1).view(np.uint8)
+        out = dst.view(torch.uint8).reshape(-1)
+        n, ch = src.shape[0], self.STAGE_CHUNK
+        nchunks = (n + ch - 1) // ch
+
+        def fill(slot, lo, hi):
+            np.copyto(views[slot][:hi - lo], src[lo:hi])
+
+        def submit(c):
+            slot = c % len(slots)
+            if used[slot]:
+                events[slot].synchronize()      # the DMA that last read this slot has finished
+            return pool.submit(fill, slot, c * ch, min(n, (c + 1) * ch))
+
+        futs = {c: submit(c) for c in range(min(len(slots), nchunks))}
+        for c in range(nchunks):
+            slot = c % len(slots)
+            futs.pop(c).result()
+            lo, hi = c * ch, min(n, (c + 1) * ch)
+            out[lo:hi].copy_(slots[slot][:hi - lo], non_blocking=True)
+            events[slot].record()
+            used[slot] = True
+            if c + len(slots) < nchunks:
+                futs[c + len(slots)] = submit(c + len(slots))
+
+    def const_device(self, arr, name):
+        """small host array that rarely changes between calls (seed grid, pairwise table, filter taps): uploaded only when its
+        content differs from what the named device buffer already holds -- no copy node in steady state, which also keeps the
+        resident pipeline capturable as a CUDA graph"""
+        arr = np.ascontiguousarray(arr)
+        key = (arr.shape, arr.dtype.str, arr.tobytes())
+        cache = self.__dict__.setdefault('_consts', {})
+        hit = cache.get(name)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        if self.torch.cuda.is_current_stream_capturing():
+            raise RuntimeError('constant %r changed while a CUDA graph is being captured' % name)
+        dst = self.to_device(arr, 'const_' + name)
+        cache[name] = (key, dst)
         return dst
 
     def pinned_empty(self, shape, dtype):
@@ -140,7 +202,7 @@ class Engine(object):
         seeds, ty, tx = slic_seed_grid(H, W, n_segments)
         n_seeds = len(seeds)
         step = float(max(1, ty, tx))
-        d_seeds = self.to_device(seeds, 'seeds')
+        d_seeds = self.const_device(seeds, 'seeds')
         wsb = lib.isb_slic_kmeans_workspace_bytes(H, W, n_seeds, ty, tx)
         ws = self.buf('ws_kmeans', (wsb,), torch.uint8)
         km = self.buf('labels_km', (H, W), torch.int32)
@@ -258,7 +320,7 @@ class Engine(object):
     def gc_energies(self, d_proba, d_edges, E, d_n_edges, d_centres, edge_mode, edge_cost, pairwise, d_n_nodes=None):
         torch, lib = self.torch, self.lib
         N, K = int(d_proba.shape[0]), int(d_proba.shape[1])
-        d_pw = self.to_device(np.ascontiguousarray(pairwise, dtype=np.float64), 'pairwise')
+        d_pw = self.const_device(np.ascontiguousarray(pairwise, dtype=np.float64), 'pairwise')
         unary = self.buf('unary', (N, K), torch.float64)
         edge_w = self.buf('edge_w', (max(E, 1),), torch.float64)
         unary_i = self.buf('unary_i', (N, K), torch.int32)

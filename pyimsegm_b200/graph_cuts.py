@@ -33,6 +33,8 @@ USE_DEVICE_GMM = True
 RANDOM_SEED = 0
 #: D <= 16 runs as one kernel (a CTA per restart), 16 < D <= 256 (colour + Leung-Malik = 189) as batched FP64 GEMMs
 DEVICE_GMM_MAX_FEATURES, DEVICE_GMM_MAX_CLASSES = 232, 8   # = DBIG of csrc/gmm.cu
+#: up to this many features the fit is one kernel without any host synchronisation (csrc/gmm.cu DMAX)
+DEVICE_GMM_SINGLE_KERNEL_MAX_FEATURES = 16
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -164,6 +164,48 @@ def _run_resident(eng, image, model, dict_features, sp_size, sp_regul, gc_regul,
     return d_segm, d_soft, (d_n_edges, cap)
 
 
+#: replay the device part of the path as ONE CUDA graph launch per image once a configuration has been seen twice (the ~70
+#: kernel launches of an image cost more host time than the GPU needs for them when images are processed back to back)
+USE_CUDA_GRAPHS = True
+_GRAPHS = {}
+
+
+def _graphable(model, dict_features, gc_regul, gc_edge_type):
+    from .graph_cuts import DEVICE_GMM_SINGLE_KERNEL_MAX_FEATURES
+    return (USE_CUDA_GRAPHS and isinstance(model, tuple) and not isinstance(gc_regul, (list, np.ndarray)) and gc_regul > 0
+            and flags_are_native(dict_features) and native_feature_layout(dict_features)[1] <= DEVICE_GMM_SINGLE_KERNEL_MAX_FEATURES
+            and all(k == 'color' for k in dict_features))
+
+
+def _run_resident_graph(eng, d_img, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type):
+    """:func:`_run_resident` for an image that already sits in ``eng``'s device buffer, captured as a CUDA graph the second time
+    a configuration is seen and replayed afterwards.  Nothing in the captured region touches the host: label and edge counts
+    stay in device scalars, the class model is fitted by the single-kernel device GMM.  Returns what ``_run_resident`` returns."""
+    if not _graphable(model, dict_features, gc_regul, gc_edge_type):
+        return _run_resident(eng, d_img, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)
+    torch = eng.torch
+    key = (id(eng), d_img.data_ptr(), tuple(d_img.shape), str(d_img.dtype), model, tuple(sorted((k, tuple(v)) for k, v in dict_features.items())),
+           sp_size, sp_regul, float(gc_regul), gc_edge_type, EDGE_CAP_PER_NODE[0])
+    entry = _GRAPHS.get(key)
+    if entry is None:          # first sight: run eagerly (this also sizes every cached buffer)
+        _GRAPHS[key] = 'seen'
+        return _run_resident(eng, d_img, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)
+    if entry == 'seen':        # second sight: capture
+        graph = torch.cuda.CUDAGraph()
+        n0 = eng.lib.isb_launch_count()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=eng.device)
+        side.wait_stream(cur)
+        with torch.cuda.graph(graph, stream=side):
+            out = _run_resident(eng, d_img, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)
+        cur.wait_stream(side)
+        entry = _GRAPHS[key] = (graph, out, int(eng.lib.isb_launch_count() - n0))
+    graph, out, n_kernels = entry
+    graph.replay()
+    eng.lib.isb_note_graph_replay(n_kernels)
+    return out
+
+
 def _download_results(eng, tensors):
     """D2H into pinned buffers with ONE synchronisation; returns numpy views"""
     outs = []
@@ -293,7 +335,8 @@ def segment_images_batch(list_images, nb_classes=None, dict_features=FTS_SET_SIM
         eng, stream = engines[i % nb_streams]
         stream.wait_stream(caller_stream)
         with torch.cuda.stream(stream):
-            d_segm, d_soft, check = _run_resident(eng, np.asarray(image), model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)
+            d_img = eng.to_device(_supported_dtype(_as_rgb_like(np.asarray(image))), 'image')
+            d_segm, d_soft, check = _run_resident_graph(eng, d_img, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)
             tensors = (d_segm, d_soft) + ((check[0], ) if check is not None else ())
             hosts = []
             for t in tensors:
@@ -373,7 +416,7 @@ def segment_resident(d_image, model, dict_features, sp_size=30, sp_regul=0.2, gc
     """ the same hot path with the image ALREADY on the device (a cuda tensor [H, W, 3]) and the results left
     there: returns (segm int32 [H, W], segm_soft float64 [H, W, K]) device tensors.  ``model`` is a callable
     proba_fn(features) or ('fit', nb_classes, use_scaler, max_iter) for the GPU-fitted default GMM. """
-    return _run_resident(get_engine(), d_image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)[:2]
+    return _run_resident_graph(get_engine(), d_image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)[:2]
 
 
 def pipe_color2d_slic_features_model_graphcut(image, nb_classes, dict_features, sp_size=30, sp_regul=0.2, pca_coef=None,

@@ -137,7 +137,7 @@ def device_lm_features(eng, d_img, d_seg, nb, flags, bank_type='normal', feat=No
         feat = eng.buf('feat_lm', (nb, ncol), torch.float64)
     H, W = int(d_seg.shape[0]), int(d_seg.shape[1])
     w_bg, radius, mix = background_kernel()
-    d_wbg = eng.to_device(w_bg, 'lm_bg_w')
+    d_wbg = eng.const_device(w_bg, 'lm_bg_w')
     wsb = lib.isb_lm_workspace_bytes(H, W, int(nb), n_batt)
     ws = eng.buf('ws_lm', (wsb,), torch.uint8)
     code = _lib.DTYPE_CODES[str(d_img.dtype).replace('torch.', '')]

@@ -154,3 +154,22 @@ def test_config3_shaped_pipeline_with_a_shared_model(oracle):
     agree = (segm == labels_o[slic_o]).mean()
     assert agree > 0.995, 'label maps agree on %.4f of the pixels' % agree
     assert np.abs(soft - proba_o[slic_o]).max() < 1e-3
+
+
+def test_cuda_graph_replay_equals_eager_launches():
+    """pipelines._run_resident_graph: the device part of the path captured once and replayed per image (batch API and
+    segment_resident) must give exactly what the eager launches give, for every image of the batch"""
+    from pyimsegm_b200 import pipelines as pl
+    imgs = [synth_regions(200, 264, seed=s)[0] for s in (31, 32, 33, 34, 35)]
+    feats = {'color': ['mean']}
+    pl.USE_CUDA_GRAPHS = False
+    try:
+        eager = pl.segment_images_batch(imgs, 3, feats, sp_size=16, sp_regul=0.2)
+    finally:
+        pl.USE_CUDA_GRAPHS = True
+    for _ in range(3):      # eager -> capture -> replay on every one of the three stream engines
+        graph = pl.segment_images_batch(imgs * 2, 3, feats, sp_size=16, sp_regul=0.2)
+    assert any(isinstance(v, tuple) for v in pl._GRAPHS.values()), 'no CUDA graph was captured'
+    for i, (segm, soft) in enumerate(graph):
+        assert np.array_equal(segm, eager[i % len(imgs)][0])
+        np.testing.assert_allclose(soft, eager[i % len(imgs)][1], rtol=1e-6, atol=1e-9)   # the statistics use floating-point atomics
