@@ -91,8 +91,8 @@ class Engine(object):
 
     #: host arrays at least this large that are NOT page-locked go through the staged upload below
     STAGE_MIN_BYTES = 4 << 20
-    STAGE_CHUNK = 8 << 20
-    STAGE_SLOTS = 4
+    STAGE_CHUNK = 4 << 20
+    STAGE_SLOTS = 8
 
     def to_device(self, arr, name=None):
         """host ndarray -> device tensor through the current stream (pinned sources copy asynchronously; large pageable sources
@@ -111,7 +111,7 @@ class Engine(object):
 
     def _staged_upload(self, dst, arr):
         """upload of a large PAGEABLE array (what a caller of the numpy API normally holds): the driver would bounce it through
-        its own small staging buffer at a fraction of the PCIe rate.  Here worker threads copy 8 MB chunks into a ring of pinned
+        its own small staging buffer at a fraction of the PCIe rate.  Here worker threads copy 4 MB chunks into a ring of pinned
         buffers (numpy releases the GIL while copying) and every chunk is sent by an asynchronous DMA as soon as it is complete, so
         the host copies overlap the transfers."""
         torch = self.torch

@@ -53,21 +53,25 @@ def all_gather_blocks(blocks, nb_items, group=None, device=None):
     # 2) payload: every rank sends one flat buffer padded to the largest per-rank payload
     sizes = np.where(all_shapes[..., 0] >= 0, all_shapes[..., 0] * all_shapes[..., 1], 0)
     cap = int(sizes.sum(axis=1).max())
-    flat = torch.zeros(max(cap, 1), dtype=torch.float64, device=device)
+    mine_flat = np.zeros(max(cap, 1), dtype=np.float64)
     off = 0
     for b in blocks:
-        t = torch.from_numpy(np.ascontiguousarray(b, dtype=np.float64).ravel())
-        flat[off:off + t.numel()] = t.to(device)
-        off += t.numel()
-    gathered = [torch.empty_like(flat) for _ in range(world)]
-    dist.all_gather(gathered, flat, group=group)
+        b = np.ascontiguousarray(b, dtype=np.float64).ravel()
+        mine_flat[off:off + b.size] = b
+        off += b.size
+    flat = torch.from_numpy(mine_flat).to(device)                  # one upload of this rank's payload ...
+    gathered = torch.empty((world, flat.numel()), dtype=torch.float64, device=device)
+    if backend == 'nccl':
+        dist.all_gather_into_tensor(gathered, flat, group=group)
+    else:
+        dist.all_gather(list(gathered.unbind(0)), flat, group=group)
+    host = gathered.cpu().numpy()                                  # ... and one download of everybody's
     out = [None] * nb_items
     for r in range(world):
-        buf = gathered[r].cpu().numpy()
         off = 0
         for slot, item in enumerate(shard_indices(nb_items, r, world)):
             rows, cols = int(all_shapes[r, slot, 0]), int(all_shapes[r, slot, 1])
-            out[item] = buf[off:off + rows * cols].reshape(rows, cols).copy()
+            out[item] = host[r, off:off + rows * cols].reshape(rows, cols).copy()
             off += rows * cols
     return out
 
@@ -80,16 +84,18 @@ def estim_model_classes_group_sharded(list_images, nb_classes, dict_features, sp
 
     :return tuple(model, list(ndarray)): the class model and ALL per-image feature blocks, identical on every rank
     """
-    if compute_features is None:
-        from .pipelines import compute_color2d_superpixels_features as compute_features
     if fit_model is None:
         from .graph_cuts import estim_class_model as fit_model
     rank, world = dist_info(group)
     mine = shard_indices(len(list_images), rank, world)
-    local = []
-    for i in mine:
-        _, fts = compute_features(list_images[i], dict_features, sp_size=sp_size, sp_regul=sp_regul)
-        local.append(np.nan_to_num(fts))
+    if compute_features is None:
+        from .pipelines import compute_features_batch
+        local = [np.nan_to_num(f) for f in compute_features_batch([list_images[i] for i in mine], dict_features, sp_size=sp_size, sp_regul=sp_regul)]
+    else:
+        local = []
+        for i in mine:
+            _, fts = compute_features(list_images[i], dict_features, sp_size=sp_size, sp_regul=sp_regul)
+            local.append(np.nan_to_num(fts))
     list_features = all_gather_blocks(local, len(list_images), group=group)
     features = np.nan_to_num(np.concatenate(tuple(list_features), axis=0))
     model = fit_model(features, nb_classes, model_type, pca_coef, use_scaler)

@@ -123,21 +123,71 @@ EARLY_SOFT_DOWNLOAD = True
 EDGE_CAP_PER_NODE = [8]
 
 
+#: replay the device part of the path as CUDA graphs once a configuration has been seen twice (the ~70 kernel launches of an image
+#: cost more host time than the GPU needs for them when images are processed back to back, and the gaps between them add up)
+USE_CUDA_GRAPHS = True
+_GRAPHS = {}
+
+
+def _graph_call(eng, key, fn):
+    """``fn()`` -- a sequence of C-ABI launches that never touches the host and writes into the engine's cached buffers -- run
+    eagerly the first time ``key`` is seen (this also sizes every buffer), captured as a CUDA graph the second time, replayed
+    afterwards.  Returns what ``fn`` returned (device tensors that every replay refills)."""
+    if not USE_CUDA_GRAPHS:
+        return fn()
+    entry = _GRAPHS.get(key)
+    if entry is None:
+        _GRAPHS[key] = 'seen'
+        return fn()
+    torch = eng.torch
+    if entry == 'seen':
+        graph = torch.cuda.CUDAGraph()
+        n0 = eng.lib.isb_launch_count()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=eng.device)
+        side.wait_stream(cur)
+        with torch.cuda.graph(graph, stream=side):
+            out = fn()
+        cur.wait_stream(side)
+        entry = _GRAPHS[key] = (graph, out, int(eng.lib.isb_launch_count() - n0))
+    graph, out, n_kernels = entry
+    graph.replay()
+    eng.lib.isb_note_graph_replay(n_kernels)
+    return out
+
+
+def _features_key(dict_features):
+    return tuple(sorted((k, tuple(v)) for k, v in dict_features.items()))
+
+
 def _run_resident(eng, image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type, soft_sink=None):
     """the whole hot path on the device.  ``model`` is either ('fit', nb_classes, use_scaler, max_iter) -> the default
     GMM is fitted on the GPU and NOTHING syncs with the host until the results are ready; or a callable
     proba_fn(features) -> one round trip (features down, probabilities up) as in the reference.
     ``soft_sink(d_seg, d_proba)``: the caller takes ``segm_soft = proba[slic]`` itself as soon as the probabilities exist
     (it does not depend on the graph cut) -- then ``d_soft`` is returned as None.
+    With a device-fitted model and colour features the two halves -- image -> class probabilities, probabilities -> cut and LUT
+    gathers -- are CUDA-graph replays (:func:`_graph_call`); the image then has to sit in one of the engine's cached buffers.
     Returns (d_segm, d_soft, check): ``check`` is None or (d_n_edges, edge_cap) still to be verified by the caller."""
-    res = _device_slic_features(eng, image, dict_features, sp_size, sp_regul)
     no_cut = (not isinstance(gc_regul, (list, np.ndarray))) and gc_regul <= 0
     if isinstance(model, tuple):
         _, nb_classes, use_scaler, max_iter = model
         from . import graph_cuts
         n_init = max(1, int(np.sqrt(max_iter)))
-        d_proba, _ = eng.gmm_fit_predict(res.d_feat, nb_classes, n_init, max_iter, use_scaler, graph_cuts.RANDOM_SEED,
-                                         d_n=res.d_n_labels)
+        if not hasattr(image, 'is_cuda'):
+            image = eng.to_device(_supported_dtype(_as_rgb_like(np.asarray(image))), 'image')
+        graphable = (USE_CUDA_GRAPHS and not no_cut and all(k == 'color' for k in dict_features) and flags_are_native(dict_features)
+                     and native_feature_layout(dict_features)[1] <= graph_cuts.DEVICE_GMM_SINGLE_KERNEL_MAX_FEATURES)
+
+        def first_half():
+            res = _device_slic_features(eng, image, dict_features, sp_size, sp_regul)
+            d_proba, _ = eng.gmm_fit_predict(res.d_feat, nb_classes, n_init, max_iter, use_scaler, graph_cuts.RANDOM_SEED,
+                                             d_n=res.d_n_labels)
+            return res, d_proba
+
+        key1 = ('probabilities', id(eng), image.data_ptr(), tuple(image.shape), str(image.dtype), model, _features_key(dict_features),
+                sp_size, sp_regul)
+        res, d_proba = _graph_call(eng, key1, first_half) if graphable else first_half()
         if no_cut:
             nb = int(eng.to_host(res.d_n_labels)[0])
             d_labels = _argmin_labels_device(eng, eng.to_host(d_proba[:nb]))
@@ -145,9 +195,16 @@ def _run_resident(eng, image, model, dict_features, sp_size, sp_regul, gc_regul,
         cap = max(64, EDGE_CAP_PER_NODE[0] * res.nb_bound)
         if soft_sink is not None:
             soft_sink(res.d_seg, d_proba)
-        _, d_segm, d_soft, d_n_edges, cap = _device_graphcut(eng, res, res.nb_bound, d_proba, nb_classes, gc_regul, gc_edge_type,
-                                                             d_n_nodes=res.d_n_labels, want_soft=soft_sink is None, edge_cap=cap)
+
+        def second_half():
+            return _device_graphcut(eng, res, res.nb_bound, d_proba, nb_classes, gc_regul, gc_edge_type, d_n_nodes=res.d_n_labels,
+                                    want_soft=soft_sink is None, edge_cap=cap)
+
+        key2 = ('cut', id(eng), res.d_seg.data_ptr(), d_proba.data_ptr(), res.d_centres.data_ptr(), res.shape, res.nb_bound, nb_classes,
+                float(gc_regul) if graphable else None, gc_edge_type, cap, soft_sink is None)
+        _, d_segm, d_soft, d_n_edges, cap = _graph_call(eng, key2, second_half) if graphable else second_half()
         return d_segm, d_soft, (d_n_edges, cap)
+    res = _device_slic_features(eng, image, dict_features, sp_size, sp_regul)
     nb = int(eng.to_host(res.d_n_labels)[0])
     features = eng.to_host(res.d_feat[:nb]).copy()
     features[np.isnan(features)] = 0
@@ -162,48 +219,6 @@ def _run_resident(eng, image, model, dict_features, sp_size, sp_regul, gc_regul,
     _, d_segm, d_soft, d_n_edges, cap = _device_graphcut(eng, res, nb, d_proba, proba.shape[1], gc_regul, gc_edge_type,
                                                          want_soft=soft_sink is None, edge_cap=cap)
     return d_segm, d_soft, (d_n_edges, cap)
-
-
-#: replay the device part of the path as ONE CUDA graph launch per image once a configuration has been seen twice (the ~70
-#: kernel launches of an image cost more host time than the GPU needs for them when images are processed back to back)
-USE_CUDA_GRAPHS = True
-_GRAPHS = {}
-
-
-def _graphable(model, dict_features, gc_regul, gc_edge_type):
-    from .graph_cuts import DEVICE_GMM_SINGLE_KERNEL_MAX_FEATURES
-    return (USE_CUDA_GRAPHS and isinstance(model, tuple) and not isinstance(gc_regul, (list, np.ndarray)) and gc_regul > 0
-            and flags_are_native(dict_features) and native_feature_layout(dict_features)[1] <= DEVICE_GMM_SINGLE_KERNEL_MAX_FEATURES
-            and all(k == 'color' for k in dict_features))
-
-
-def _run_resident_graph(eng, d_img, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type):
-    """:func:`_run_resident` for an image that already sits in ``eng``'s device buffer, captured as a CUDA graph the second time
-    a configuration is seen and replayed afterwards.  Nothing in the captured region touches the host: label and edge counts
-    stay in device scalars, the class model is fitted by the single-kernel device GMM.  Returns what ``_run_resident`` returns."""
-    if not _graphable(model, dict_features, gc_regul, gc_edge_type):
-        return _run_resident(eng, d_img, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)
-    torch = eng.torch
-    key = (id(eng), d_img.data_ptr(), tuple(d_img.shape), str(d_img.dtype), model, tuple(sorted((k, tuple(v)) for k, v in dict_features.items())),
-           sp_size, sp_regul, float(gc_regul), gc_edge_type, EDGE_CAP_PER_NODE[0])
-    entry = _GRAPHS.get(key)
-    if entry is None:          # first sight: run eagerly (this also sizes every cached buffer)
-        _GRAPHS[key] = 'seen'
-        return _run_resident(eng, d_img, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)
-    if entry == 'seen':        # second sight: capture
-        graph = torch.cuda.CUDAGraph()
-        n0 = eng.lib.isb_launch_count()
-        cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream(device=eng.device)
-        side.wait_stream(cur)
-        with torch.cuda.graph(graph, stream=side):
-            out = _run_resident(eng, d_img, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)
-        cur.wait_stream(side)
-        entry = _GRAPHS[key] = (graph, out, int(eng.lib.isb_launch_count() - n0))
-    graph, out, n_kernels = entry
-    graph.replay()
-    eng.lib.isb_note_graph_replay(n_kernels)
-    return out
 
 
 def _download_results(eng, tensors):
@@ -335,8 +350,7 @@ def segment_images_batch(list_images, nb_classes=None, dict_features=FTS_SET_SIM
         eng, stream = engines[i % nb_streams]
         stream.wait_stream(caller_stream)
         with torch.cuda.stream(stream):
-            d_img = eng.to_device(_supported_dtype(_as_rgb_like(np.asarray(image))), 'image')
-            d_segm, d_soft, check = _run_resident_graph(eng, d_img, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)
+            d_segm, d_soft, check = _run_resident(eng, np.asarray(image), model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)
             tensors = (d_segm, d_soft) + ((check[0], ) if check is not None else ())
             hosts = []
             for t in tensors:
@@ -346,6 +360,45 @@ def segment_images_batch(list_images, nb_classes=None, dict_features=FTS_SET_SIM
             event = torch.cuda.Event()
             event.record(stream)
         pending.append((i, hosts, event, check))
+        while len(pending) > max_in_flight:
+            _finish(pending.pop(0))
+    while pending:
+        _finish(pending.pop(0))
+    return results
+
+
+def compute_features_batch(list_images, dict_features, sp_size=30, sp_regul=0.2, nb_streams=3, max_in_flight=6):
+    """ superpixel features of a LIST of images (the per-image half of ``estim_model_classes_group``, which the reference hands to
+    a process pool, pipelines.py:139-147): consecutive images alternate over ``nb_streams`` CUDA streams with their own buffers,
+    nothing synchronises with the host until an image's feature table is downloaded
+
+    :return list(ndarray): features [N_i, D] per image, in input order
+    """
+    if not flags_are_native(dict_features) or any(np.ndim(im) != 3 for im in list_images):
+        return [compute_color2d_superpixels_features(im, dict_features, sp_size=sp_size, sp_regul=sp_regul)[1] for im in list_images]
+    engines = _batch_engines(nb_streams)
+    torch = engines[0][0].torch
+    results, pending = [None] * len(list_images), []
+
+    def _finish(item):
+        idx, h_feat, h_n, event = item
+        event.synchronize()
+        features = h_feat.numpy()[:int(h_n.numpy()[0])].copy()
+        features[np.isnan(features)] = 0
+        results[idx] = features
+
+    caller_stream = torch.cuda.current_stream()
+    for i, image in enumerate(list_images):
+        eng, stream = engines[i % nb_streams]
+        stream.wait_stream(caller_stream)
+        with torch.cuda.stream(stream):
+            res = _device_slic_features(eng, np.asarray(image), dict_features, sp_size, sp_regul)
+            h_feat, h_n = eng.pinned_empty(res.d_feat.shape, res.d_feat.dtype), eng.pinned_empty((1, ), torch.int32)
+            h_feat.copy_(res.d_feat, non_blocking=True)
+            h_n.copy_(res.d_n_labels, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record(stream)
+        pending.append((i, h_feat, h_n, event))
         while len(pending) > max_in_flight:
             _finish(pending.pop(0))
     while pending:
@@ -416,7 +469,7 @@ def segment_resident(d_image, model, dict_features, sp_size=30, sp_regul=0.2, gc
     """ the same hot path with the image ALREADY on the device (a cuda tensor [H, W, 3]) and the results left
     there: returns (segm int32 [H, W], segm_soft float64 [H, W, K]) device tensors.  ``model`` is a callable
     proba_fn(features) or ('fit', nb_classes, use_scaler, max_iter) for the GPU-fitted default GMM. """
-    return _run_resident_graph(get_engine(), d_image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)[:2]
+    return _run_resident(get_engine(), d_image, model, dict_features, sp_size, sp_regul, gc_regul, gc_edge_type)[:2]
 
 
 def pipe_color2d_slic_features_model_graphcut(image, nb_classes, dict_features, sp_size=30, sp_regul=0.2, pca_coef=None,
@@ -447,10 +500,7 @@ def estim_model_classes_group(list_images, nb_classes, dict_features, sp_size=30
 
     :return tuple(model, list(ndarray)): fitted sklearn pipeline, list of per-image features
     """
-    list_features = []
-    for image in list_images:
-        _, features = compute_color2d_superpixels_features(image, dict_features, sp_size=sp_size, sp_regul=sp_regul)
-        list_features.append(features)
+    list_features = compute_features_batch(list_images, dict_features, sp_size=sp_size, sp_regul=sp_regul)
     features = np.nan_to_num(np.concatenate(tuple(list_features), axis=0))
     model = estim_class_model(features, nb_classes, model_type, pca_coef, use_scaler)
     return model, list_features
