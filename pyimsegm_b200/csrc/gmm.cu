@@ -74,13 +74,14 @@ __device__ double block_sum_d(double v, double* s_red)
     return t;
 }
 
-// StandardScaler: mean / population std per feature (zero variance -> scale 1), single CTA
+// StandardScaler: mean / population std per feature (zero variance -> scale 1), one CTA per feature
 __global__ void __launch_bounds__(GT) k_gmm_scale(const double* __restrict__ feat, int N_in, const int* n_dev, int D, int ld, int use_scaler,
                                                   GmmWs w)
 {
     __shared__ double s_red[GT / 32];
     const int N = n_dev ? min(*n_dev, N_in) : N_in;
-    for (int d = 0; d < D; ++d) {
+    {
+        const int d = blockIdx.x;
         double s = 0;
         for (int n = threadIdx.x; n < N; n += GT) s += feat[(size_t)n * ld + d];
         double mean = block_sum_d(s, s_red) / N;
@@ -121,10 +122,52 @@ __device__ __forceinline__ double log_prob_all(const double* x, int D, int K, co
     return mx + log(s);
 }
 
-// parameters from responsibilities (sklearn _estimate_gaussian_parameters + _compute_precision_cholesky)
-// returns false when a covariance is not positive definite
-__device__ bool m_step(const double* __restrict__ xs, const double* __restrict__ resp, int N, int D, int K, double reg, double* par,
-                       double* s_part, double* s_red)
+// ---- the single-kernel path (D <= DMAX): one thread-block CLUSTER of CL CTAs per restart ------------------------------------------
+// The samples of a restart are cut into CL contiguous ranges, one per CTA of the cluster.  Every CTA keeps a bit-identical replica of
+// the model parameters in its shared memory; what crosses the CTAs are the partial sums of the reductions (log-likelihood, component
+// weights / means / covariances, k-means counts), exchanged through distributed shared memory and added in rank order by every CTA,
+// so the replicas never diverge.  CL = 1 is the plain one-CTA-per-restart kernel (small N).
+
+struct ClusterCtx {
+    int rank, CL;
+    double* s_x;      // [GT] exchange buffer of this CTA (remote CTAs read it through DSMEM)
+    double* s_red;    // [GT / 32]
+};
+
+// every thread contributes `v`; every thread of every CTA of the cluster gets the same total (partials added in rank order)
+__device__ double cluster_sum(double v, const ClusterCtx& c)
+{
+    const double t = block_sum_d(v, c.s_red);
+    if (c.CL == 1) return t;
+    cg::cluster_group cl = cg::this_cluster();
+    if (threadIdx.x == 0) c.s_x[0] = t;
+    cl.sync();
+    double tot = 0;
+    for (int r = 0; r < c.CL; ++r) tot += *cl.map_shared_rank(&c.s_x[0], r);
+    cl.sync();
+    return tot;
+}
+
+// threads [0, nq) hold one partial each (their quantity's sum over this CTA's samples); returns the cluster-wide sum of the
+// thread's quantity (partials added in rank order).  Collective: every thread of every CTA must call it.
+__device__ double cluster_vec_sum(double part, int nq, const ClusterCtx& c)
+{
+    if (c.CL == 1) return part;
+    cg::cluster_group cl = cg::this_cluster();
+    if ((int)threadIdx.x < nq) c.s_x[threadIdx.x] = part;
+    cl.sync();
+    double tot = 0;
+    if ((int)threadIdx.x < nq)
+        for (int r = 0; r < c.CL; ++r) tot += *cl.map_shared_rank(&c.s_x[threadIdx.x], r);
+    cl.sync();
+    return tot;
+}
+
+// parameters from responsibilities (sklearn _estimate_gaussian_parameters + _compute_precision_cholesky) over the samples
+// [n_lo, n_hi) of this CTA, merged over the cluster; `par` is this CTA's shared-memory replica.
+// returns false when a covariance is not positive definite (the same answer in every CTA)
+__device__ bool m_step(const double* __restrict__ xs, const double* __restrict__ resp, int n_lo, int n_hi, int N, int D, int K, double reg,
+                       double* par, double* s_part, const ClusterCtx& c)
 {
     double* wts = par; double* mu = par + K; double* cov = mu + K * D; double* pc = cov + (size_t)K * D * D;
     // pass 1: nk and means, quantity-parallel over sample slices
@@ -136,16 +179,18 @@ __device__ bool m_step(const double* __restrict__ xs, const double* __restrict__
         double acc = 0;
         if (sl < S) {
             const int k = q / (1 + D), j = q % (1 + D);
-            for (int n = sl; n < N; n += S) {
+            for (int n = n_lo + sl; n < n_hi; n += S) {
                 double r = resp[(size_t)n * K + k];
                 acc += j == 0 ? r : r * xs[(size_t)n * D + j - 1];
             }
         }
         s_part[threadIdx.x] = acc;
         __syncthreads();
-        if (threadIdx.x < nq) {
-            double t = 0;
+        double t = 0;
+        if ((int)threadIdx.x < nq)
             for (int s2 = 0; s2 < S; ++s2) t += s_part[s2 * nq + threadIdx.x];
+        t = cluster_vec_sum(t, nq, c);
+        if ((int)threadIdx.x < nq) {
             const int k = q / (1 + D), j = q % (1 + D);
             if (j == 0) wts[k] = t + 10 * DBL_EPSILON; // nk (divided by N at the end)
             else mu[k * D + j - 1] = t;                 // sum r x (divided by nk below)
@@ -166,17 +211,19 @@ __device__ bool m_step(const double* __restrict__ xs, const double* __restrict__
         double acc = 0;
         if (sl < S) {
             const double ma = mu[k * D + a], mb = mu[k * D + b];
-            for (int n = sl; n < N; n += S)
+            for (int n = n_lo + sl; n < n_hi; n += S)
                 acc += resp[(size_t)n * K + k] * (xs[(size_t)n * D + a] - ma) * (xs[(size_t)n * D + b] - mb);
         }
         s_part[threadIdx.x] = acc;
         __syncthreads();
-        if (threadIdx.x < nq) {
-            double tt = 0;
+        double tt = 0;
+        if ((int)threadIdx.x < nq)
             for (int s2 = 0; s2 < S; ++s2) tt += s_part[s2 * nq + threadIdx.x];
-            double c = tt / wts[k] + (a == b ? reg : 0.0);
-            cov[(size_t)k * D * D + a * D + b] = c;
-            cov[(size_t)k * D * D + b * D + a] = c;
+        tt = cluster_vec_sum(tt, nq, c);
+        if ((int)threadIdx.x < nq) {
+            double cc = tt / wts[k] + (a == b ? reg : 0.0);
+            cov[(size_t)k * D * D + a * D + b] = cc;
+            cov[(size_t)k * D * D + b * D + a] = cc;
         }
         __syncthreads();
     }
@@ -200,12 +247,12 @@ __device__ bool m_step(const double* __restrict__ xs, const double* __restrict__
         if (!ok) s_bad = 1;
         else {
             // Z = L^-1 (lower);  U = Z^T
-            for (int c = 0; c < D; ++c)
+            for (int cc = 0; cc < D; ++cc)
                 for (int r = 0; r < D; ++r) {
-                    if (r < c) { U[c * D + r] = 0.0; continue; }
-                    double s = (r == c) ? 1.0 : 0.0;
-                    for (int p = c; p < r; ++p) s -= L[r * D + p] * U[c * D + p]; // U[c][p] holds Z[p][c]
-                    U[c * D + r] = s / L[r * D + r];
+                    if (r < cc) { U[cc * D + r] = 0.0; continue; }
+                    double s = (r == cc) ? 1.0 : 0.0;
+                    for (int p = cc; p < r; ++p) s -= L[r * D + p] * U[cc * D + p]; // U[cc][p] holds Z[p][cc]
+                    U[cc * D + r] = s / L[r * D + r];
                 }
         }
     }
@@ -215,27 +262,34 @@ __device__ bool m_step(const double* __restrict__ xs, const double* __restrict__
     return s_bad == 0;
 }
 
-// one CTA per restart
+// one cluster of CL CTAs per restart (gridDim.x = n_init * CL, cluster dimension CL set at launch)
 __global__ void __launch_bounds__(GT) k_gmm_fit(int N_in, const int* n_dev, int D, int K, int max_iter, double tol, double reg,
-                                               unsigned long long seed, const int* __restrict__ init_labels, GmmWs w)
+                                               unsigned long long seed, const int* __restrict__ init_labels, int CL, GmmWs w)
 {
+    extern __shared__ double s_dyn[];          // parameter replica [pstride(K, D)]
     __shared__ double s_part[GT];
+    __shared__ double s_x[GT];
     __shared__ double s_red[GT / 32];
     __shared__ double s_logdet[KMAX];
     __shared__ double s_cent[KMAX * DMAX];
+    __shared__ double s_tot[KMAX * (1 + DMAX)];
     __shared__ int s_pick;
     const int N = n_dev ? min(*n_dev, N_in) : N_in;
-    const int init = blockIdx.x;
+    const int init = blockIdx.x / CL;
+    ClusterCtx c;
+    c.rank = blockIdx.x % CL; c.CL = CL; c.s_x = s_x; c.s_red = s_red;
+    const int chunk_n = (N + CL - 1) / CL;
+    const int n_lo = min(N, c.rank * chunk_n), n_hi = min(N, n_lo + chunk_n);   // the samples of this CTA
     const double* xs = w.xs;
     double* resp = w.resp + (size_t)init * N_in * K;
     int* lab = w.lab + (size_t)init * N_in;
-    double* par = w.par + (size_t)init * pstride(K, D);
+    double* par = s_dyn;
+    double* gpar = w.par + (size_t)init * pstride(K, D);
     double* wts = par; double* mu = par + K; double* pc = mu + K * D + (size_t)K * D * D;
-    double* tail = par + K + K * D + 2 * (size_t)K * D * D; // lower_bound, n_iter, converged, ok
 
     // ---- initial hard assignment ----
     if (init_labels) {
-        for (int n = threadIdx.x; n < N; n += GT) lab[n] = init_labels[(size_t)init * N_in + n];
+        for (int n = n_lo + threadIdx.x; n < n_hi; n += GT) lab[n] = init_labels[(size_t)init * N_in + n];
         __syncthreads();
     } else {
         // k-means++ seeding (one D^2-weighted draw per centre), then Lloyd
@@ -244,44 +298,69 @@ __global__ void __launch_bounds__(GT) k_gmm_fit(int N_in, const int* n_dev, int 
         int first = (int)(rng.uniform() * N); if (first >= N) first = N - 1;
         for (int d = threadIdx.x; d < D; d += GT) s_cent[d] = xs[(size_t)first * D + d];
         __syncthreads();
-        for (int c = 1; c <= K; ++c) {
-            // update closest distances with centre c-1
+        for (int cc = 1; cc <= K; ++cc) {
+            // update closest distances with centre cc-1
             double loc = 0;
-            for (int n = threadIdx.x; n < N; n += GT) {
+            for (int n = n_lo + threadIdx.x; n < n_hi; n += GT) {
                 double s = 0;
-                for (int d = 0; d < D; ++d) { double t = xs[(size_t)n * D + d] - s_cent[(c - 1) * D + d]; s += t * t; }
-                double cur = (c == 1) ? s : fmin(d2[n], s);
+                for (int d = 0; d < D; ++d) { double t = xs[(size_t)n * D + d] - s_cent[(cc - 1) * D + d]; s += t * t; }
+                double cur = (cc == 1) ? s : fmin(d2[n], s);
                 d2[n] = cur;
                 loc += cur;
             }
-            double total = block_sum_d(loc, s_red);
-            if (c == K) break;
-            const double thr = rng.uniform() * total; // same on every thread (same rng state)
-            // contiguous chunks -> prefix over chunk sums -> the chunk holding thr scans itself
-            const int chunk = (N + GT - 1) / GT, beg = threadIdx.x * chunk, end = min(beg + chunk, N);
+            // total over the cluster AND the running sum of the ranks before this one (the draw walks the samples in order)
+            const double mine = block_sum_d(loc, s_red);
+            double total = mine, before = 0;
+            if (CL > 1) {
+                cg::cluster_group cl = cg::this_cluster();
+                if (threadIdx.x == 0) s_x[0] = mine;
+                cl.sync();
+                total = 0;
+                for (int r = 0; r < CL; ++r) { const double pr = *cl.map_shared_rank(&s_x[0], r); if (r < c.rank) before += pr; total += pr; }
+                cl.sync();
+            }
+            if (cc == K) break;
+            const double thr = rng.uniform() * total; // same on every thread of every CTA (same rng state)
+            // the CTA whose range holds thr: contiguous per-thread chunks -> prefix over chunk sums -> the chunk holding thr scans itself
+            const bool holder = (thr > before || c.rank == 0) && (thr <= before + mine || c.rank == CL - 1);
+            const int nloc = n_hi - n_lo;
+            const int chunk = (nloc + GT - 1) / GT, beg = n_lo + threadIdx.x * chunk, end = min(beg + chunk, n_hi);
             double cs = 0;
             for (int n = beg; n < end; ++n) cs += d2[n];
             s_part[threadIdx.x] = cs;
-            if (threadIdx.x == 0) s_pick = N - 1;
+            if (threadIdx.x == 0) s_pick = -1;
             __syncthreads();
-            if (threadIdx.x == 0) {
-                double run = 0; int t = 0;
+            if (threadIdx.x == 0 && holder && nloc > 0) {
+                double run = before; int t = 0;
                 for (; t < GT; ++t) { if (run + s_part[t] >= thr) break; run += s_part[t]; }
+                int pick = n_hi - 1;
                 if (t < GT) {
-                    int b2 = t * chunk, e2 = min(b2 + chunk, N), n = b2;
+                    int b2 = n_lo + t * chunk, e2 = min(b2 + chunk, n_hi), n = b2;
                     for (; n < e2; ++n) { run += d2[n]; if (run >= thr) break; }
-                    s_pick = min(n, N - 1);
+                    pick = min(n, n_hi - 1);
                 }
+                s_pick = pick;
             }
             __syncthreads();
-            for (int d = threadIdx.x; d < D; d += GT) s_cent[c * D + d] = xs[(size_t)s_pick * D + d];
+            // the lowest-ranked CTA that made a pick publishes it (rounding may make two neighbours claim the threshold)
+            int pick = s_pick;
+            if (CL > 1) {
+                cg::cluster_group cl = cg::this_cluster();
+                if (threadIdx.x == 0) s_x[1] = (double)s_pick;
+                cl.sync();
+                pick = -1;
+                for (int r = 0; r < CL && pick < 0; ++r) pick = (int)*cl.map_shared_rank(&s_x[1], r);
+                cl.sync();
+            }
+            if (pick < 0) pick = N - 1;
+            for (int d = threadIdx.x; d < D; d += GT) s_cent[cc * D + d] = xs[(size_t)pick * D + d];
             __syncthreads();
         }
         // Lloyd iterations (sklearn KMeans: max_iter 300, tol 1e-4 * mean feature variance; X is standardised)
-        for (int n = threadIdx.x; n < N; n += GT) lab[n] = -1;
+        for (int n = n_lo + threadIdx.x; n < n_hi; n += GT) lab[n] = -1;
         for (int it = 0; it < 300; ++it) {
             int changed = 0;
-            for (int n = threadIdx.x; n < N; n += GT) {
+            for (int n = n_lo + threadIdx.x; n < n_hi; n += GT) {
                 double best = DBL_MAX; int bk = 0;
                 for (int k = 0; k < K; ++k) {
                     double s = 0;
@@ -290,37 +369,36 @@ __global__ void __launch_bounds__(GT) k_gmm_fit(int N_in, const int* n_dev, int 
                 }
                 if (lab[n] != bk) { lab[n] = bk; changed = 1; }
             }
-            changed = __syncthreads_or(changed);
             // new centres: count and coordinate sums of every cluster in ONE quantity-parallel pass over sample slices
-            // (quantity q = (k, j): j == 0 the count, j >= 1 the sum of coordinate j-1)
-            const int Q = K * (1 + D);                 // <= 8 * 17 = 136 <= GT
-            const int S = max(1, GT / Q);
+            // (quantity q = (k, j): j == 0 the count, j >= 1 the sum of coordinate j-1); quantity Q carries the "changed" flag
+            const int Q = K * (1 + D);                 // <= 8 * 17 = 136 < GT
+            const int S = max(1, GT / (Q + 1));
             {
-                const int q = threadIdx.x % Q, sl = threadIdx.x / Q;
+                const int q = threadIdx.x % (Q + 1), sl = threadIdx.x / (Q + 1);
                 double a = 0;
-                if (sl < S) {
+                if (sl < S && q < Q) {
                     const int k = q / (1 + D), j = q % (1 + D);
-                    for (int n = sl; n < N; n += S)
+                    for (int n = n_lo + sl; n < n_hi; n += S)
                         if (lab[n] == k) a += j == 0 ? 1.0 : xs[(size_t)n * D + j - 1];
                 }
                 s_part[threadIdx.x] = a;
             }
+            changed = __syncthreads_or(changed);
+            double t = 0;
+            if ((int)threadIdx.x < Q) { for (int s2 = 0; s2 < S; ++s2) t += s_part[s2 * (Q + 1) + threadIdx.x]; }
+            else if ((int)threadIdx.x == Q) t = changed ? 1.0 : 0.0;
+            t = cluster_vec_sum(t, Q + 1, c);
+            if ((int)threadIdx.x <= Q) s_tot[threadIdx.x] = t;
             __syncthreads();
-            __shared__ double s_tot[KMAX * (1 + DMAX)];
-            if (threadIdx.x < Q) {
-                double t = 0;
-                for (int s2 = 0; s2 < S; ++s2) t += s_part[s2 * Q + threadIdx.x];
-                s_tot[threadIdx.x] = t;
-            }
-            __syncthreads();
+            changed = s_tot[Q] != 0.0;
             double shift = 0;
             for (int k = 0; k < K; ++k) {
                 const double cnt = s_tot[k * (1 + D)];
                 if (cnt > 0)
-                    for (int d = 0; d < D; ++d) { const double t = s_tot[k * (1 + D) + 1 + d] / cnt - s_cent[k * D + d]; shift += t * t; }
+                    for (int d = 0; d < D; ++d) { const double tt = s_tot[k * (1 + D) + 1 + d] / cnt - s_cent[k * D + d]; shift += tt * tt; }
             }
             __syncthreads();
-            if (threadIdx.x < K * D) {
+            if ((int)threadIdx.x < K * D) {
                 const int k = threadIdx.x / D, d = threadIdx.x % D;
                 const double cnt = s_tot[k * (1 + D)];
                 if (cnt > 0) s_cent[threadIdx.x] = s_tot[k * (1 + D) + 1 + d] / cnt;
@@ -330,11 +408,11 @@ __global__ void __launch_bounds__(GT) k_gmm_fit(int N_in, const int* n_dev, int 
         }
         __syncthreads();
     }
-    for (int i = threadIdx.x; i < N * K; i += GT) resp[i] = (lab[i / K] == i % K) ? 1.0 : 0.0;
+    for (int i = n_lo * K + threadIdx.x; i < n_hi * K; i += GT) resp[i] = (lab[i / K] == i % K) ? 1.0 : 0.0;
     __syncthreads();
 
     // ---- EM ----
-    bool ok = m_step(xs, resp, N, D, K, reg, par, s_part, s_red);
+    bool ok = m_step(xs, resp, n_lo, n_hi, N, D, K, reg, par, s_part, c);
     double lower = -DBL_MAX;
     int it = 0, conv = 0;
     if (ok) {
@@ -347,20 +425,29 @@ __global__ void __launch_bounds__(GT) k_gmm_fit(int N_in, const int* n_dev, int 
             }
             __syncthreads();
             double acc = 0;
-            for (int n = threadIdx.x; n < N; n += GT) {
+            for (int n = n_lo + threadIdx.x; n < n_hi; n += GT) {
                 double lw[KMAX];
                 double lse = log_prob_all(xs + (size_t)n * D, D, K, wts, mu, pc, s_logdet, lw);
                 for (int k = 0; k < K; ++k) resp[(size_t)n * K + k] = exp(lw[k] - lse);
                 acc += lse;
             }
-            lower = block_sum_d(acc, s_red) / N;
-            ok = m_step(xs, resp, N, D, K, reg, par, s_part, s_red);
+            lower = cluster_sum(acc, c) / N;
+            ok = m_step(xs, resp, n_lo, n_hi, N, D, K, reg, par, s_part, c);
             if (!ok) break;
             if (it > 1 && fabs(lower - prev) < tol) { conv = 1; break; }
         }
         if (it > max_iter) it = max_iter;
     }
-    if (threadIdx.x == 0) { tail[0] = ok ? lower : -DBL_MAX; tail[1] = (double)it; tail[2] = (double)conv; tail[3] = ok ? 1.0 : 0.0; }
+    // rank 0 publishes the replica (every replica is identical) and the outcome of the restart
+    if (c.rank == 0) {
+        const int np = K + K * D + 2 * K * D * D;
+        for (int i = threadIdx.x; i < np; i += GT) gpar[i] = par[i];
+        if (threadIdx.x == 0) {
+            double* tail = gpar + np; // lower_bound, n_iter, converged, ok
+            tail[0] = ok ? lower : -DBL_MAX; tail[1] = (double)it; tail[2] = (double)conv; tail[3] = ok ? 1.0 : 0.0;
+        }
+    }
+    if (CL > 1) cg::this_cluster().sync();   // no CTA may exit while a neighbour can still read its exchange buffer
 }
 
 
@@ -1058,9 +1145,19 @@ extern "C" int isb_gmm_fit_predict(const double* feat, int N, int D, int ld, con
         }
         // every restart failed: fall through to k_gmm_predict, which reports it (NaN probabilities, ok = 0)
     } else {
-        k_gmm_scale<<<1, GT, 0, st>>>(feat, N, n_dev, D, ld, use_scaler, w);
+        k_gmm_scale<<<D, GT, 0, st>>>(feat, N, n_dev, D, ld, use_scaler, w);
         ISB_LAUNCH_CHECK();
-        k_gmm_fit<<<n_init, GT, 0, st>>>(N, n_dev, D, K, max_iter, tol, reg_covar, seed, init_labels, w);
+        // one thread-block cluster per restart; the cluster size follows the (upper bound of the) sample count
+        const int CL = N <= 1024 ? 1 : (N <= 4096 ? 2 : (N <= 16384 ? 4 : 8));
+        const size_t par_bytes = sizeof(double) * (size_t)pstride(K, D);
+        ISB_CUDA_CHECK(cudaFuncSetAttribute(k_gmm_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)par_bytes));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(n_init * CL); cfg.blockDim = dim3(GT); cfg.dynamicSmemBytes = par_bytes; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        ISB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gmm_fit, N, n_dev, D, K, max_iter, tol, reg_covar, seed, init_labels, CL, w));
         ISB_LAUNCH_CHECK();
     }
     int blocks = (N + 255) / 256;
