@@ -97,6 +97,29 @@ def synth_texture_image(seed, h=H, w=W, n_classes=4, cell=64):
     return np.clip(img + rng.normal(0, 0.03, img.shape), 0, 1)
 
 
+def synth_eggs_image(seed, h=640, w=1024, n_eggs=6):
+    """config-4 style image (the reference's drosophila ovary slices are 1024 x 647): elliptic 'eggs' of random
+    size and orientation, brighter than a noisy background.  Returns (image [H, W, 3], annotation [H, W] with egg i as label i + 1,
+    centres)"""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[:h, :w].astype(np.float64)
+    annot = np.zeros((h, w), dtype=int)
+    centres = []
+    cols = np.linspace(0, w, n_eggs // 2 + 2)[1:-1]
+    for i in range(n_eggs):
+        cy = h * (0.3 if i % 2 == 0 else 0.72) + rng.uniform(-0.04, 0.04) * h
+        cx = cols[i // 2] + rng.uniform(-0.03, 0.03) * w
+        a, b = rng.uniform(0.10, 0.13) * w * 0.8, rng.uniform(0.14, 0.19) * h * 0.8
+        ang = rng.uniform(0, np.pi)
+        u = (xx - cx) * np.cos(ang) + (yy - cy) * np.sin(ang)
+        v = -(xx - cx) * np.sin(ang) + (yy - cy) * np.cos(ang)
+        inside = (u / a) ** 2 + (v / b) ** 2 <= 1.0
+        annot[inside & (annot == 0)] = i + 1
+        centres.append((int(round(cy)), int(round(cx))))
+    img = np.where(annot > 0, 0.7, 0.25)[..., None] + np.array([0.0, 0.03, -0.03])
+    return np.clip(img + rng.normal(0, 0.06, img.shape), 0, 1), annot, centres
+
+
 def load_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.isfile(path):
@@ -599,6 +622,66 @@ def run_texture(args):
         dist.destroy_process_group()
 
 
+def run_rg2sp(args):
+    """extra workload (not the headline line): BASELINE config 4 -- region growing with a shape prior on superpixels (RG2SP) on an
+    ovary-like synthetic image (the reference's drosophila slices do not travel to the GPU box): class segmentation by the hot
+    path, SLIC superpixels, a shape model from Ray features, then the growing loop whose every step is a device graph cut."""
+    import torch
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback)'
+    torch.cuda.set_device(local)
+    if rank != 0:
+        return
+    from pyimsegm_b200 import _lib, pipelines, region_growing as rg, superpixels
+    lib = _lib.lib()
+    h, w = 640, 1024
+    img, annot, centres = synth_eggs_image(4000, h, w)
+    list_rays, _ = rg.compute_object_shapes([(annot == i + 1) for i in range(len(centres))], ray_step=10, interp_order='spline', smooth_coef=1)
+    chist = rg.transform_rays_model_cdf_histograms(np.round(list_rays).astype(int), nb_bins=12)
+    start = [(c[0] + 5, c[1] - 6) for c in centres]
+    times = {'class_segmentation': 0.0, 'superpixels': 0.0, 'region_growing': 0.0}
+
+    def step():
+        t0 = time.perf_counter()
+        segm, _ = pipelines.pipe_color2d_slic_features_model_graphcut(img, 2, FEATURES, sp_size=25, sp_regul=0.2)
+        fg = int(np.bincount(segm[annot > 0]).argmax())            # which of the two unsupervised classes is the eggs
+        t1 = time.perf_counter()
+        slic = superpixels.segment_slic_img2d(img, sp_size=15, relative_compact=0.3)
+        t2 = time.perf_counter()
+        prob = rg.compute_segm_prob_fg(slic, (segm == fg).astype(int), [0.1, 0.9])
+        history = {}
+        labels = rg.region_growing_shape_slic_graphcut(slic, prob, start, (None, chist), 'cdf', coef_shape=2., coef_pairwise=5.,
+                                                       prob_label_trans=[0.1, 0.03], nb_iter=150, debug_history=history)
+        t3 = time.perf_counter()
+        times['class_segmentation'] += t1 - t0; times['superpixels'] += t2 - t1; times['region_growing'] += t3 - t2
+        return labels[slic], len(history['criteria'])
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    for k in times:
+        times[k] = 0.0
+    n0 = lib.isb_launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        objects, n_steps = step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    jac = []
+    for i in range(len(centres)):
+        a, b = objects == i + 1, annot == i + 1
+        jac.append(float((a & b).sum()) / float((a | b).sum()))
+    line = {'metric': METRIC, 'value': h * w / 1e6 / dt, 'unit': 'MPix/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': max(args.warmup, 1),
+            'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'config4: %dx%d ovary-like synthetic image, 6 eggs; 2-class SLIC+GMM+GraphCut segmentation, SLIC sp_size=15 '
+                                   'superpixels, RG2SP region growing with a Ray-feature shape prior (one device graph cut per growing step)' % (h, w),
+                       'timed': 'host image in, object label map out, wall clock (the growing loop is host driven)'},
+            'e2e': {'value': h * w / 1e6 / dt, 'unit': 'MPix/s', 'h2d_bytes_per_step': int(2 * img.nbytes), 'd2h_bytes_per_step': int(objects.nbytes)},
+            'gpu_launches': int(lib.isb_launch_count() - n0), 'growing_steps': int(n_steps),
+            'ms_per_stage': {k: v / args.steps * 1e3 for k, v in times.items()}, 'jaccard_per_egg': jac,
+            'cpu_baseline': None, 'reference_libs': probe_reference_libs()}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -607,7 +690,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-images', type=int, default=4, help='images in the bounded cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--workload', default='config2', choices=['config2', 'config3', 'config5'],
+    ap.add_argument('--workload', default='config2', choices=['config2', 'config3', 'config4', 'config5'],
                     help='config2 = the headline line (default); config5 = one 8192x8192 image banded over the GPUs (extra)')
     ap.add_argument('--tiled-side', type=int, default=8192)
     args = ap.parse_args()
@@ -617,6 +700,8 @@ def main():
         run_tiled(args)
     elif args.workload == 'config3':
         run_texture(args)
+    elif args.workload == 'config4':
+        run_rg2sp(args)
     else:
         run_ours(args)
 

@@ -291,6 +291,18 @@ int isb_lm_texture(const void* img, int dtype, const int32_t* seg, int H, int W,
  * variant 0 = the descriptor convention the library uses; 1 = leading/stride byte offsets swapped (diagnostic only). */
 int isb_umma_selftest(const float* A, const float* B, int N, int K, int variant, float* D, isb_stream_t stream);
 
+/* per-segment, per-channel median -- numpy_img2d_color_median (imsegm/descriptors.py:420-455, channels = 3, n_px = H*W) and
+ * numpy_img3d_gray_median (:651-676, channels = 1, n_px = D*H*W); np.median semantics (mean of the two middle values for an even
+ * count), NaN for a label without pixels.
+ *   img : [n_px, channels] interleaved, dtype = isb_dtype;  seg : [n_px] labels in [0, nb);  out : [nb, channels] f64 */
+size_t isb_segment_median_workspace_bytes(long long n_px, int nb);
+int isb_segment_median(const void* img, int dtype, const int32_t* seg, long long n_px, int channels, int nb, double* out, void* ws,
+                       size_t ws_bytes, isb_stream_t stream);
+
+/* skimage.morphology.opening(mask, disk(radius)) of a binary mask as imsegm/descriptors.py:1873-1876 applies it before tracing Ray
+ * features: erosion then dilation with a disc, borders reflected.  mask / tmp / out : [H, W] uint8 (0 / 1) */
+int isb_binary_opening_disk(const uint8_t* mask, int H, int W, int radius, uint8_t* tmp, uint8_t* out, isb_stream_t stream);
+
 /* dst[0..n) = value (initial labeling of isb_alpha_expansion and similar small fills) */
 int isb_fill_i32(int32_t* dst, long long n, int32_t value, isb_stream_t stream);
 

@@ -143,21 +143,31 @@ def numpy_img2d_color_energy(img, seg):
     return _host_label_sums(img ** 2, seg, nb) / cnt[:, None]
 
 
+def _device_median(img, seg, channels):
+    """per-label median of every channel on the device (``isb_segment_median``: counting sort by label + radix select)"""
+    import ctypes as C
+    from . import _lib
+    eng = get_engine()
+    img = _device_dtype(img)
+    n_px = int(seg.size)
+    nb = int(seg.max()) + 1
+    d_img = eng.to_device(img, 'median_img')
+    d_seg = eng.to_device(np.ascontiguousarray(seg, dtype=np.int32), 'seg_in')
+    out = eng.buf('median_out', (nb, channels), eng.torch.float64)
+    wsb = eng.lib.isb_segment_median_workspace_bytes(C.c_longlong(n_px), nb)
+    ws = eng.buf('ws_median', (wsb,), eng.torch.uint8)
+    code = _lib.DTYPE_CODES[str(img.dtype)]
+    _lib.check(eng.lib.isb_segment_median(_lib.ptr(d_img), code, _lib.ptr(d_seg), C.c_longlong(n_px), channels, nb, _lib.ptr(out), _lib.ptr(ws),
+                                          C.c_size_t(wsb), _lib.stream_ptr()))
+    return eng.to_host(out).copy()
+
+
 def numpy_img2d_color_median(img, seg):
-    """ per-segment, per-channel median (reference descriptors.py:420-455; no native path exists there either) """
+    """ per-segment, per-channel median (reference descriptors.py:420-455: a pure-Python loop over the pixels there, no native
+    path); NaN for labels without pixels """
     img, seg = np.asarray(img), np.asarray(seg)
     _check_color_image_segm(img, seg)
-    nb = int(seg.max()) + 1
-    flat = seg.ravel()
-    order = np.argsort(flat, kind='stable')
-    bounds = np.searchsorted(flat[order], np.arange(nb + 1))
-    medians = np.full((nb, 3), np.nan)
-    for c in range(3):
-        vals = img[..., c].ravel()[order]
-        for lb in range(nb):
-            if bounds[lb + 1] > bounds[lb]:
-                medians[lb, c] = np.median(vals[bounds[lb]:bounds[lb + 1]])
-    return medians
+    return _device_median(img, seg, 3)
 
 
 def _device_gray_stats(img, seg, flags):
@@ -284,16 +294,7 @@ def numpy_img3d_gray_median(img, seg):
     """ median intensity per segment of a gray volume (reference descriptors.py:651-676; NaN for absent labels) """
     img, seg = np.asarray(img), np.asarray(seg)
     _check_gray_image_segm(img, seg)
-    nb = int(seg.max()) + 1
-    flat = seg.ravel()
-    order = np.argsort(flat, kind='stable')
-    bounds = np.searchsorted(flat[order], np.arange(nb + 1))
-    vals = img.ravel()[order]
-    medians = np.full(nb, np.nan)
-    for lb in range(nb):
-        if bounds[lb + 1] > bounds[lb]:
-            medians[lb] = np.median(vals[bounds[lb]:bounds[lb + 1]])
-    return medians
+    return _device_median(img, seg, 1)[:, 0]
 
 
 def compute_image3d_gray_statistic(image, segm, feature_flags=NAMES_FEATURE_FLAGS, ch_name='gray'):
@@ -656,10 +657,9 @@ def compute_ray_features_positions(segm, list_positions, angle_step=5., border_l
     border_labels = border_labels if border_labels is not None else [0]
     if segm.ndim > pos_dim:
         segm = np.argmax(segm, axis=-1)
-    if isinstance(segm_open, int):
-        raise NotImplementedError('segm_open (a morphological opening of the boundary mask, skimage.morphology.opening in the '
-                                  'reference) is not provided; open the mask beforehand')
     seg_binary = np.isin(segm, list(border_labels))
+    if isinstance(segm_open, int):
+        seg_binary = binary_opening_disk(seg_binary, segm_open)     # skimage.morphology.opening(mask, disk(r)) on the device
     positions = [tuple(map(int, pos)) for pos in list_positions]
     rays = np.atleast_2d(cython_ray_features_seg2d(seg_binary, np.asarray(positions), angle_step, edge))
     pos_rays, pos_shift = [], []
@@ -676,6 +676,71 @@ def compute_ray_features_positions(segm, list_positions, angle_step=5., border_l
     if pos_rays.shape[1] != len(feature_names):
         raise ValueError('Ray features: %r and names %r' % (pos_rays.shape, feature_names))
     return pos_rays, pos_shift, feature_names
+
+
+def binary_opening_disk(mask, radius):
+    """ morphological opening of a binary 2-D mask with a disc of ``radius`` pixels, borders reflected -- what the reference gets
+    from ``skimage.morphology.opening(mask, morphology.disk(radius))`` (descriptors.py:1873-1876); ``isb_binary_opening_disk`` """
+    from . import _lib
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    if mask.ndim != 2:
+        raise ValueError('expected a 2-D mask, got shape %r' % (mask.shape, ))
+    eng = get_engine()
+    d_in = eng.to_device(mask, 'morph_in')
+    tmp = eng.buf('morph_tmp', mask.shape, eng.torch.uint8)
+    out = eng.buf('morph_out', mask.shape, eng.torch.uint8)
+    _lib.check(eng.lib.isb_binary_opening_disk(_lib.ptr(d_in), mask.shape[0], mask.shape[1], int(radius), _lib.ptr(tmp), _lib.ptr(out),
+                                               _lib.stream_ptr()))
+    return eng.to_host(out).astype(bool)
+
+
+def compute_ray_features_segm_2d_vectors(seg_binary, position, angle_step=5., smooth_coef=0, edge='up'):
+    """ the reference's legacy Ray tracer (descriptors.py:1545-1625, "USES WHOLE IMAGE ROTATION SO IT IS VERY SLOW"): the mask is
+    shifted so that ``position`` is the image centre and rotated (nearest neighbour) once per angle; the distances are read along the
+    four half-axes of every rotated copy.  Kept for API completeness on scipy's ``ndimage.shift`` / ``rotate`` like the original --
+    it is not on any accelerated path; :func:`compute_ray_features_segm_2d` is the device tracer.
+
+    :return ndarray: distances, -1 where no boundary is met
+    """
+    from scipy import ndimage
+    seg_binary = np.asarray(seg_binary).astype(bool)
+    angle_range = 90 if (90 % angle_step) == 0 else 180
+    nb_steps = int(angle_range / angle_step)
+    ray_dist = np.full(int(nb_steps * 2 * (180 / angle_range)), -1)
+    if bool(seg_binary[int(position[0]), int(position[1])]) and edge == 'up':
+        return ray_dist * 0            # the position already sits on the boundary label
+    size = np.array(seg_binary.shape)
+    shift = size / 2 - np.asarray(position)
+    pad = np.abs(shift).astype(int)
+    canvas = np.zeros(size + 2 * pad)
+    canvas[pad[0]:pad[0] + size[0], pad[1]:pad[1] + size[1]] = seg_binary
+    centred = ndimage.shift(canvas, shift.tolist(), order=0, cval=True)
+
+    def first_edge(line):
+        """distance to the first boundary pixel ('up') or to the end of the first boundary run ('down') along a half-axis"""
+        hits = np.flatnonzero(line)
+        if not hits.size:
+            return None
+        if edge == 'up':
+            return int(hits[0])
+        if edge == 'down':
+            gaps = np.flatnonzero(~line[hits[0]:])
+            return int(hits[0] + gaps[0]) if gaps.size else None
+        return None
+
+    for i, ang in enumerate(np.arange(0, angle_range, angle_step)):
+        rot = ndimage.rotate(centred, ang + 90, order=0, reshape=True, cval=True).astype(bool)
+        cy, cx = (np.array(rot.shape) / 2).astype(int)
+        half_axes = [rot[:cy, cx][::-1], rot[cy, cx:], rot[cy:, cx], rot[cy, :cx][::-1]]
+        if angle_range == 180:
+            half_axes = [half_axes[0], half_axes[2]]
+        for j, line in enumerate(half_axes):
+            dist = first_edge(line)
+            if dist is not None:
+                ray_dist[i + j * nb_steps] = dist
+    if smooth_coef > 0:
+        ray_dist = ndimage.gaussian_filter1d(ray_dist, smooth_coef)
+    return np.array(ray_dist)
 
 
 def interpolate_ray_dist(ray_dists, order='spline'):

@@ -463,33 +463,54 @@ def segment_graph_cut_general(segments, proba, image=None, features=None, gc_reg
     return graph_labels
 
 
+def _canonical_int_edges(edges, w_i):
+    """pairs as (a, b) with a < b, self loops dropped, parallel edges merged by adding their (already integer) weights -- the energy
+    GCO builds when ``setNeighbors`` is called for both orders or twice for the same pair"""
+    edges = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+    lo, hi = edges.min(axis=1), edges.max(axis=1)
+    keep = lo != hi
+    lo, hi, w_i = lo[keep], hi[keep], np.asarray(w_i, dtype=np.int64)[keep]
+    if not len(lo):
+        return np.zeros((0, 2), np.int32), np.zeros(0, np.intc)
+    key = lo * (int(hi.max()) + 1) + hi
+    uniq, inverse = np.unique(key, return_inverse=True)
+    if len(uniq) == len(key) and (edges[keep][:, 0] < edges[keep][:, 1]).all():
+        return np.ascontiguousarray(edges[keep], dtype=np.int32), np.ascontiguousarray(w_i, dtype=np.intc)
+    merged_w = np.bincount(inverse, weights=w_i.astype(np.float64), minlength=len(uniq))
+    first = np.zeros(len(uniq), dtype=np.int64)
+    first[inverse[::-1]] = np.arange(len(key))[::-1]                      # first occurrence of every pair
+    order = np.argsort(first, kind='stable')
+    out = np.stack([lo[first], hi[first]], axis=1)[order]
+    return np.ascontiguousarray(out, dtype=np.int32), np.ascontiguousarray(np.minimum(merged_w[order], 2 ** 31 - 1), dtype=np.intc)
+
+
 def cut_general_graph(edges, edge_weights, unary_cost, pairwise_cost, n_iter=-1, algorithm='expansion', init_labels=None,
                       down_weight_factor=None):
     """ drop-in for ``gco.cut_general_graph`` (pyGCO) as the reference calls it (graph_cuts.py:735-744,
-    region_growing.py:148,1698): float energies are integerised like pyGCO does, alpha-expansion runs on the GPU
+    region_growing.py:148,1698): float energies are integerised like pyGCO does, alpha-expansion runs on the GPU.  Edges may come in
+    either orientation and more than once (region_growing.py:1433-1444 lists an edge from both of its ends): parallel edges add up.
 
     :return ndarray: labels int32 [N]
     """
     if algorithm != 'expansion':
         raise NotImplementedError('only algorithm="expansion" is used by the reference hot path')
     eng = get_engine()
-    torch = eng.torch
-    edges = np.ascontiguousarray(edges, dtype=np.int32)
-    if len(edges) and not (edges[:, 0] < edges[:, 1]).all():
-        raise ValueError('edges must be given as (a, b) with a < b')
     w = np.asarray(edge_weights)
     un = np.asarray(unary_cost)
     pw = np.asarray(pairwise_cost)
     is_float = any(a.dtype.kind == 'f' for a in (w, un, pw))
     if is_float:
         if down_weight_factor is None:
-            down_weight_factor = max(np.abs(un).max(), np.abs(w).max() * pw.max()) + 1e-10
+            down_weight_factor = max(np.abs(un).max(), (np.abs(w).max() if w.size else 0.) * pw.max()) + 1e-10
         un_i = (un / down_weight_factor * 100000).astype(np.intc)
         w_i = (w / down_weight_factor * 1000).astype(np.intc)
         pw_i = (pw * 100).astype(np.intc)
     else:
         un_i, w_i, pw_i = un.astype(np.intc), w.astype(np.intc), pw.astype(np.intc)
+    edges, w_i = _canonical_int_edges(edges, w_i)
     N, K = un_i.shape
+    if len(edges) and int(edges.max()) >= N:
+        raise ValueError('an edge refers to vertex %d, the unary table has %d rows' % (int(edges.max()), N))
     E = len(edges)
     d_edges = eng.to_device(edges if E else np.zeros((1, 2), np.int32), 'edges_in')
     d_w = eng.to_device(np.ascontiguousarray(w_i) if E else np.zeros(1, np.intc), 'edge_wi_in')
@@ -500,6 +521,22 @@ def cut_general_graph(edges, edge_weights, unary_cost, pairwise_cost, n_iter=-1,
         init = eng.to_device(np.ascontiguousarray(init_labels, dtype=np.int32), 'init_labels')
     labels, _, _ = eng.alpha_expansion(N, K, E, None, d_edges, d_w, d_un, d_pw, int(n_iter), init)
     return eng.to_host(labels).copy()
+
+
+def cut_grid_graph(unary_cost, pairwise_cost, cost_v, cost_h, n_iter=-1, algorithm='expansion'):
+    """ drop-in for ``gco.cut_grid_graph`` (pyGCO) as the reference calls it (region_growing.py:248): alpha-expansion over the
+    4-connected pixel grid, ``cost_v[y, x]`` weighting the edge (y, x)-(y+1, x) and ``cost_h[y, x]`` the edge (y, x)-(y, x+1)
+
+    :param ndarray unary_cost: [H, W, K]
+    :return ndarray: labels int32 [H * W]
+    """
+    unary_cost = np.asarray(unary_cost)
+    height, width, nb_labels = unary_cost.shape
+    idx = np.arange(height * width).reshape(height, width)
+    edges = np.concatenate([np.stack([idx[:-1].ravel(), idx[1:].ravel()], 1), np.stack([idx[:, :-1].ravel(), idx[:, 1:].ravel()], 1)])
+    weights = np.concatenate([np.asarray(cost_v, dtype=float).ravel(), np.asarray(cost_h, dtype=float).ravel()])
+    return cut_general_graph(edges, weights, unary_cost.reshape(-1, nb_labels), pairwise_cost, n_iter=n_iter, algorithm=algorithm,
+                             down_weight_factor=1.0)
 
 
 def count_label_transitions_connected_segments(dict_slics, dict_labels, nb_labels=None):

@@ -75,8 +75,14 @@ def test_ray_features_positions_reference_doctest(oracle):
     np.testing.assert_allclose(single, oracle.ray_features2d(seg == 0, points[1], 20., 1), rtol=1e-6)
     smooth = ds.compute_ray_features_segm_2d(seg == 0, points[0], 10, smooth_coef=2)
     assert smooth.shape == (36, ) and np.all(np.abs(np.diff(smooth)) < 4)
-    with pytest.raises(NotImplementedError):
-        ds.compute_ray_features_positions(seg, points, 45, segm_open=10)
+    # descriptors.py:1846-1858: salt noise on the mask, removed by the opening with a disc of radius 10 (device morphology)
+    np.random.seed(0)
+    noise_pos = np.random.randint(10, 80, (2, 300))
+    seg[noise_pos[0], noise_pos[1]] = 0
+    ray_dist, shift, names = ds.compute_ray_features_positions(seg, points, 45, segm_open=10)
+    assert names == ['ray-lb_0-agl_%d' % a for a in range(0, 360, 45)]
+    assert [int(round(s)) for s in shift] == [315, 315, 90]
+    assert ray_dist.astype(int).tolist() == [[38, 35, 29, 25, 24, 25, 29, 35], [52, 41, 21, 11, 9, 11, 21, 41], [31, 31, 30, 29, 29, 29, 30, 31]]
 
 
 def test_gray_volume_statistics_reference_doctest():
@@ -154,3 +160,42 @@ def test_supervised_data_step_labels_follow_the_annotation():
     assert np.all(labels[np.unique(slic[:8])] == -1)          # superpixels inside the unknown strip
     with pytest.raises(NotImplementedError):
         pl.train_classif_color2d_slic_features([img], [annot], {'color': ['mean']})
+
+
+def test_binary_opening_equals_scipy_grey_opening():
+    """isb_binary_opening_disk: erosion then dilation with a disc, reflected borders (what skimage.morphology.opening does on a
+    boolean image through scipy.ndimage.grey_erosion / grey_dilation)"""
+    from scipy import ndimage
+    from pyimsegm_b200 import descriptors as ds
+    rng = np.random.RandomState(3)
+    mask = ndimage.gaussian_filter(rng.random_sample((70, 95)), 2) > 0.5
+    for radius in (1, 3, 6):
+        yy, xx = np.mgrid[-radius:radius + 1, -radius:radius + 1]
+        disk = (yy ** 2 + xx ** 2) <= radius ** 2
+        want = ndimage.grey_dilation(ndimage.grey_erosion(mask.astype(np.uint8), footprint=disk), footprint=disk).astype(bool)
+        assert np.array_equal(ds.binary_opening_disk(mask, radius), want)
+
+
+def test_segment_median_on_the_device(oracle):
+    """isb_segment_median against np.median per label (reference descriptors.py:420-455, 651-676), odd and even counts, every dtype,
+    an absent label; and the reference's doctest values (:429-437)"""
+    from pyimsegm_b200 import descriptors as ds
+    image = np.zeros((2, 10, 3))
+    image[:, 2:6, 0] = 1
+    image[:, 3:8, 1] = 3
+    image[:, 4:9, 2] = 2
+    segm = np.array([[0, 0, 0, 0, 1, 1, 1, 1, 1, 1]] * 2)
+    np.testing.assert_allclose(ds.numpy_img2d_color_median(image, segm), [[0.5, 0., 0.], [0., 3., 2.]])
+    rng = np.random.RandomState(5)
+    seg = rng.randint(0, 41, (60, 77))
+    seg[seg == 17] = 18                      # label 17 is absent -> NaN
+    for dtype in (np.float64, np.float32, np.uint8, np.uint16):
+        img = (rng.random_sample((60, 77, 3)) * 200).astype(dtype)
+        got = ds.numpy_img2d_color_median(img, seg)
+        want = oracle.color2d_median(img, seg)
+        assert np.isnan(got[17]).all()
+        np.testing.assert_array_equal(np.delete(got, 17, 0), np.delete(want, 17, 0))
+    vol = rng.random_sample((4, 20, 30))
+    vseg = rng.randint(0, 9, vol.shape)
+    want = np.array([np.median(vol[vseg == k]) for k in range(9)])
+    np.testing.assert_array_equal(ds.numpy_img3d_gray_median(vol, vseg), want)
