@@ -85,6 +85,9 @@ class Engine(object):
         n = int(np.prod(shape)) if shape else 1
         cur = self._bufs.get(name)
         if cur is None or cur.dtype != dtype or cur.numel() < n:
+            if cur is not None and getattr(self, 'graphs_captured', 0):
+                # a captured CUDA graph may hold the address of the old block: keep it alive instead of returning it to the allocator
+                self.__dict__.setdefault('_retired', []).append(cur)
             cur = torch.empty(max(n, 1), dtype=dtype, device=self.device)
             self._bufs[name] = cur
         return cur[:n].view(shape)
@@ -147,19 +150,20 @@ class Engine(object):
                 futs[c + len(slots)] = submit(c + len(slots))
 
     def const_device(self, arr, name):
-        """small host array that rarely changes between calls (seed grid, pairwise table, filter taps): uploaded only when its
-        content differs from what the named device buffer already holds -- no copy node in steady state, which also keeps the
-        resident pipeline capturable as a CUDA graph"""
+        """small host array that rarely changes between calls (seed grid, pairwise table, filter taps): every distinct content gets
+        its OWN device tensor, uploaded once and never overwritten -- no copy in steady state, and a captured CUDA graph that read
+        one of them keeps reading the right values whatever other configurations run in between"""
+        import hashlib
         arr = np.ascontiguousarray(arr)
-        key = (arr.shape, arr.dtype.str, arr.tobytes())
+        key = (name, arr.shape, arr.dtype.str, hashlib.blake2b(arr.tobytes(), digest_size=16).digest())
         cache = self.__dict__.setdefault('_consts', {})
-        hit = cache.get(name)
-        if hit is not None and hit[0] == key:
-            return hit[1]
+        hit = cache.get(key)
+        if hit is not None:
+            return hit
         if self.torch.cuda.is_current_stream_capturing():
-            raise RuntimeError('constant %r changed while a CUDA graph is being captured' % name)
-        dst = self.to_device(arr, 'const_' + name)
-        cache[name] = (key, dst)
+            raise RuntimeError('constant %r is new while a CUDA graph is being captured' % name)
+        dst = self.torch.from_numpy(arr).to(self.device)
+        cache[key] = dst
         return dst
 
     def pinned_empty(self, shape, dtype):

@@ -149,6 +149,7 @@ def _graph_call(eng, key, fn):
         with torch.cuda.graph(graph, stream=side):
             out = fn()
         cur.wait_stream(side)
+        eng.graphs_captured = getattr(eng, 'graphs_captured', 0) + 1      # from now on the engine never frees a buffer it outgrows
         entry = _GRAPHS[key] = (graph, out, int(eng.lib.isb_launch_count() - n0))
     graph, out, n_kernels = entry
     graph.replay()

@@ -72,7 +72,7 @@ def test_object_shapes_golden():
     assert np.array(list_rays).astype(int).tolist() == [[19, 17, 9, 17, 19, 14, 19, 14], [29, 21, 28, 20, 28, 20, 28, 21],
                                                        [22, 16, 21, 15, 21, 15, 21, 16], [22, 16, 21, 15, 21, 15, 21, 16],
                                                        [22, 16, 21, 15, 21, 15, 21, 16]]
-    assert (np.array(list_shifts) % 180).tolist() == [135., 45., 45., 45., 45.]
+    np.testing.assert_allclose(np.array(list_shifts) % 180, [135., 45., 45., 45., 45.], atol=1e-4)
 
 
 def test_segm_prob_fg_golden():

@@ -173,3 +173,19 @@ def test_cuda_graph_replay_equals_eager_launches():
     for i, (segm, soft) in enumerate(graph):
         assert np.array_equal(segm, eager[i % len(imgs)][0])
         np.testing.assert_allclose(soft, eager[i % len(imgs)][1], rtol=1e-6, atol=1e-9)   # the statistics use floating-point atomics
+
+
+def test_graph_replay_survives_other_configurations_in_between():
+    """a captured graph keeps its own constants (seed grid) and buffers: running another image size / superpixel size on the same
+    engine between two replays must not change what the replay computes"""
+    from pyimsegm_b200 import pipelines as pl
+    img, _ = synth_regions(160, 208, seed=41)
+    other, _ = synth_regions(300, 260, seed=42)
+    feats = {'color': ['mean']}
+    runs = [pl.pipe_color2d_slic_features_model_graphcut(img, 3, feats, sp_size=16, sp_regul=0.2) for _ in range(3)]   # eager, capture, replay
+    pl.pipe_color2d_slic_features_model_graphcut(other, 3, feats, sp_size=20, sp_regul=0.3)          # grows buffers, new seed grid
+    pl.compute_color2d_superpixels_features(other, feats, sp_size=11, sp_regul=0.2)
+    again = pl.pipe_color2d_slic_features_model_graphcut(img, 3, feats, sp_size=16, sp_regul=0.2)
+    for segm, soft in runs[1:] + [again]:
+        assert np.array_equal(segm, runs[0][0])
+        np.testing.assert_allclose(soft, runs[0][1], rtol=1e-6, atol=1e-9)
