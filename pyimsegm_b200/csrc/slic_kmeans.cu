@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(ATHREADS, 5) k_assign(const __grid_constant__ 
     __shared__ Cand cand[ACAP];
     __shared__ double s_maxdc[SLICO ? ACAP : 1];
     __shared__ float s_key[ACAP];
+    __shared__ float2 s_cf[ACAP];         // (cy, cx) of the candidate as floats, for the per-thread spatial lower bound
     __shared__ double s_lb[ACAP];          // lower bound of the spatial term of the candidate at sorted position i, and of all later ones
     __shared__ unsigned char s_order[ACAP];
     __shared__ __align__(128) double s_px[3][TILE][TILE]; // Lab of the tile
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(ATHREADS, 5) k_assign(const __grid_constant__ 
                         if (SLICO) s_maxdc[pos] = s.packed_maxdc[i];
                         const float fy = (float)c.cy - tcy, fx = (float)c.cx - tcx;
                         s_key[pos] = fy * fy + fx * fx;
+                        s_cf[pos] = make_float2((float)c.cy, (float)c.cx);
                     }
                 }
             }
@@ -267,6 +269,7 @@ __global__ void __launch_bounds__(ATHREADS, 5) k_assign(const __grid_constant__ 
                         if (SLICO) s_maxdc[pos] = s.packed_maxdc[i];
                         const float fy = (float)c.cy - tcy, fx = (float)c.cx - tcx;
                         s_key[pos] = fy * fy + fx * fx;
+                        s_cf[pos] = make_float2((float)c.cy, (float)c.cx);
                     }
                     n += __popc(m);
                     int adv = min(min(32, room), end - beg);
@@ -299,12 +302,24 @@ __global__ void __launch_bounds__(ATHREADS, 5) k_assign(const __grid_constant__ 
         if (use_tma) umma::mbar_wait(umma::smem_u32(&s_bar), 0);   // phase 0 completes once; later rounds pass immediately
         if (xin) {
             const double xd = (double)x;
+            // this thread's pixels: column x, AROWS consecutive rows: the float form of the column and the centre of the run
+            const float xf = (float)x, ymid = (float)(yb + s.y_off) + 0.5f * (AROWS - 1), swf = (float)s.sw * 0.998f;
             unsigned long long worst = dbits(DBL_MAX); // max over the rows of the current minima (bit pattern)
 #pragma unroll
             for (int j = 0; j < AROWS; ++j) worst = max(worst, dbits(best[j]));
+            float worstf = __double2float_ru(__longlong_as_double((long long)worst));
             for (int ci = 0; ci < nc; ++ci) {
                 if (dbits(s_lb[ci]) > worst) break; // sorted by key: nobody further down the list can win either
                 const int c = s_order[ci];
+                {
+                    // spatial lower bound of this candidate for ALL of the thread's pixels, in float: the centre is at least
+                    // |cx - x| away in x and |cy - ymid| - (AROWS-1)/2 in y.  2e-3 px absorbs the float conversion of coordinates
+                    // up to 16k, the factor 0.998 the rounding of the few float operations: the bound can only come out smaller
+                    // than the exact double distance term, so it never rejects a candidate that could win or tie
+                    const float2 cf = s_cf[c];
+                    const float ax = fmaxf(fabsf(cf.y - xf) - 2e-3f, 0.f), ay = fmaxf(fabsf(cf.x - ymid) - (0.5f * (AROWS - 1) + 2e-3f), 0.f);
+                    if ((ax * ax + ay * ay) * swf > worstf) continue;
+                }
                 const int cx0 = cand[c].x0, cx1 = cand[c].x1;
                 if (x < cx0 || x >= cx1) continue;
                 const int cy0 = cand[c].y0, ck = cand[c].k;
@@ -338,6 +353,7 @@ __global__ void __launch_bounds__(ATHREADS, 5) k_assign(const __grid_constant__ 
                     worst = 0;
 #pragma unroll
                     for (int j = 0; j < AROWS; ++j) if (yb + j < s.H) worst = max(worst, dbits(best[j]));
+                    worstf = __double2float_ru(__longlong_as_double((long long)worst));
                 }
             }
         }
