@@ -497,15 +497,12 @@ __global__ void __launch_bounds__(256) k_dgemm_batched(const double* __restrict_
     if (b_upper) k_end = min(k_end, n0 + TN);
     const double* sr = FUSE_W ? fw.sresp + br * fw.sr_r + bk : nullptr;          // sr[n * K]
     const double* mu = FUSE_W ? fw.mu + br * fw.mu_r + (size_t)bk * fw.D : nullptr;
-    // FP64 tensor cores: mma.sync m8n8k4 (DMMA).  8 warps as 2 (M) x 4 (N), a warp owns 32 x 16 of the 64 x 64 tile = 4 x 2 MMA tiles
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;
-    const int fr = lane >> 2, fk = lane & 3;            // fragment row (A) / column (B), fragment k
-    double acc[4][2][2];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
     double ra[4], rb[4];
     auto gload = [&](int k0) {
 #pragma unroll
@@ -536,35 +533,28 @@ __global__ void __launch_bounds__(256) k_dgemm_batched(const double* __restrict_
         __syncthreads();
         if (k0 + TK < k_end) gload(k0 + TK);
 #pragma unroll
-        for (int k4 = 0; k4 < TK; k4 += 4) {
-            double a[4], bb[2];
+        for (int kk = 0; kk < TK; ++kk) {
+            double a[4], bb[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[k4 + fk][wm + 8 * i + fr];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) bb[j] = Bs[k4 + fk][wn + 8 * j + fr];
+            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; bb[i] = Bs[kk][tx * 4 + i]; }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
-                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                                 : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
-                                 : "d"(a[i]), "d"(bb[j]));
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int gm = m0 + wm + 8 * i + fr;
+        const int gm = m0 + ty * 4 + i;
         if (gm >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int gn = n0 + wn + 8 * j + 2 * fk;
-            if (gn < Nn) C[(size_t)gm * ldc + gn] = acc[i][j][0];
-            if (gn + 1 < Nn) C[(size_t)gm * ldc + gn + 1] = acc[i][j][1];
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn < Nn) C[(size_t)gm * ldc + gn] = acc[i][j];
         }
     }
 }
-
 
 // StandardScaler for many features: one CTA per 32 features, warps over the samples, lanes over the features; per-warp partials
 // are added in warp order (k_gmm_scale walks the features one by one -- fine for D <= 16, 2.4 ms at D = 189)
