@@ -10,6 +10,8 @@
 //   pyGCO cut_general_graph        float -> int conversion (see oracle/gc_oracle.cpp header)
 //   imsegm/pipelines.py:104,109    proba[slic], graph_labels[slic]
 #include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -194,20 +196,38 @@ __device__ double block_max(double v, double* s_red)
     return t;
 }
 
-// single CTA per graph.  vfeat [N, D]: the per-vertex vectors the edge metric compares (proba for 'model').
-__global__ void __launch_bounds__(1024) k_gc_energies(const double* __restrict__ proba, int N_in, const int* n_nodes_dev, int K, const int* __restrict__ edges, int E_in,
+constexpr int ECL = 8;   // CTAs of the energy kernel's thread-block cluster
+
+// the four global quantities of the energy construction (largest unary, mean / deviation of the edge distances, largest weight) are
+// reduced over the cluster through distributed shared memory: partials added / compared in rank order, the same value in every CTA
+__device__ double cluster_reduce(double v, bool is_max, double* s_red, double* s_x)
+{
+    const double t = is_max ? block_max(v, s_red) : block_sum(v, s_red);
+    cg::cluster_group cl = cg::this_cluster();
+    if (threadIdx.x == 0) *s_x = t;
+    cl.sync();
+    double tot = is_max ? -1.0 : 0.0;
+    for (int r = 0; r < ECL; ++r) { const double pr = *cl.map_shared_rank(s_x, r); tot = is_max ? fmax(tot, pr) : tot + pr; }
+    cl.sync();
+    return tot;
+}
+
+// one cluster of ECL CTAs per graph.  vfeat [N, D]: the per-vertex vectors the edge metric compares (proba for 'model').
+__global__ void __cluster_dims__(ECL, 1, 1) __launch_bounds__(1024) k_gc_energies(const double* __restrict__ proba, int N_in, const int* n_nodes_dev, int K, const int* __restrict__ edges, int E_in,
                                                       const int* n_edges_dev, const double* __restrict__ centres,
                                                       const double* __restrict__ vfeat, int D, int metric, int spatial,
                                                       double edge_cost, const double* __restrict__ pairwise, double* unary,
                                                       double* edge_w, int* unary_i, int* edge_wi, int* smooth_i, double* sp)
 {
     __shared__ double s_red[32];
+    __shared__ double s_x;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;   // the cluster is the whole grid
     // an overflowed edge table (count > capacity) holds unspecified rows: no edge is read, the host redoes the image
     const int E = n_edges_dev ? (*n_edges_dev > E_in ? 0 : *n_edges_dev) : E_in;
     const int N = n_nodes_dev ? min(*n_nodes_dev, N_in) : N_in;
     // unary = |-log(clip(p, 0.01, 0.99))|
     double umax = 0.0;
-    for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
+    for (int i = tid; i < N * K; i += nth) {
         double p = proba[i];
         if (p < 0.01) p = 0.01;
         if (p > 1.0 - 0.01) p = 1.0 - 0.01;
@@ -215,10 +235,10 @@ __global__ void __launch_bounds__(1024) k_gc_energies(const double* __restrict__
         unary[i] = u;
         umax = fmax(umax, fabs(u));
     }
-    umax = block_max(umax, s_red);
+    umax = cluster_reduce(umax, true, s_red, &s_x);
     // edge distances
     double dsum = 0.0, ssum = 0.0;
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    for (int e = tid; e < E; e += nth) {
         int a = edges[2 * e], b = edges[2 * e + 1];
         double dist = 0.0;
         if (metric != 0) {
@@ -241,17 +261,17 @@ __global__ void __launch_bounds__(1024) k_gc_energies(const double* __restrict__
             ssum += s;
         }
     }
-    dsum = block_sum(dsum, s_red);
-    ssum = block_sum(ssum, s_red);
+    dsum = cluster_reduce(dsum, false, s_red, &s_x);
+    ssum = cluster_reduce(ssum, false, s_red, &s_x);
     const double dmean = E > 0 ? dsum / E : 0.0, smean = E > 0 ? ssum / E : 1.0;
     double vsum = 0.0;
     if (metric != 0)
-        for (int e = threadIdx.x; e < E; e += blockDim.x) { double t = edge_w[e] - dmean; vsum += t * t; }
-    vsum = block_sum(vsum, s_red);
+        for (int e = tid; e < E; e += nth) { double t = edge_w[e] - dmean; vsum += t * t; }
+    vsum = cluster_reduce(vsum, false, s_red, &s_x);
     const double sd = sqrt(E > 0 ? vsum / E : 0.0);
     const double denom = 2.0 * (sd * sd);
     double wmax = 0.0;
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    for (int e = tid; e < E; e += nth) {
         double wv = metric != 0 ? exp(-edge_w[e] / denom) : 1.0;
         if (spatial) wv = wv / (sp[e] / smean);
         if (wv < 1e-3) wv = 1e-3;
@@ -260,15 +280,14 @@ __global__ void __launch_bounds__(1024) k_gc_energies(const double* __restrict__
         edge_w[e] = wv;
         wmax = fmax(wmax, fabs(wv));
     }
-    wmax = block_max(wmax, s_red);
+    wmax = cluster_reduce(wmax, true, s_red, &s_x);
     double pmax = pairwise[0];
     for (int i = 1; i < K * K; ++i) pmax = fmax(pmax, pairwise[i]);
     // pyGCO: down_weight_factor = max(|unary|.max(), |w|.max() * pairwise.max()) + 1e-10
     const double dwf = fmax(umax, wmax * pmax) + 1e-10;
-    __syncthreads();
-    for (int i = threadIdx.x; i < N * K; i += blockDim.x) unary_i[i] = (int)((unary[i] / dwf) * 100000.0);
-    for (int e = threadIdx.x; e < E; e += blockDim.x) edge_wi[e] = (int)((edge_w[e] / dwf) * 1000.0);
-    for (int i = threadIdx.x; i < K * K; i += blockDim.x) smooth_i[i] = (int)(pairwise[i] * 100.0);
+    for (int i = tid; i < N * K; i += nth) unary_i[i] = (int)((unary[i] / dwf) * 100000.0);
+    for (int e = tid; e < E; e += nth) edge_wi[e] = (int)((edge_w[e] / dwf) * 1000.0);
+    for (int i = tid; i < K * K; i += nth) smooth_i[i] = (int)(pairwise[i] * 100.0);
 }
 
 // ------------------------------------------------------------------ gathers --------------------------------------------------------
@@ -373,7 +392,7 @@ extern "C" int isb_gc_energies(const double* proba, int N, const int32_t* n_node
     ISB_REQUIRE(!spatial || centres, "centres are required for spatially normalised edge weights");
     ISB_REQUIRE(ws_bytes >= isb_gc_energies_workspace_bytes(N, K, E), "workspace too small");
     ProfScope prof(ISB_PROF_ENERGY, (cudaStream_t)stream);
-    k_gc_energies<<<1, 1024, 0, (cudaStream_t)stream>>>(proba, N, n_nodes_dev, K, edges, E, n_edges_dev, centres, proba, K, metric, spatial, edge_cost,
+    k_gc_energies<<<ECL, 1024, 0, (cudaStream_t)stream>>>(proba, N, n_nodes_dev, K, edges, E, n_edges_dev, centres, proba, K, metric, spatial, edge_cost,
                                                          pairwise, unary, edge_w, unary_i, edge_wi, smooth_i, (double*)ws);
     ISB_LAUNCH_CHECK();
     return ISB_OK;

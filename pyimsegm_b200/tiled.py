@@ -331,36 +331,51 @@ def pipe_color2d_slic_features_model_graphcut_tiled(image, nb_classes, dict_feat
             nb = int(res.nb_bound)
             d_proba, _ = eng.gmm_fit_predict(res.d_feat, K, n_init, max_iter, use_scaler, graph_cuts.RANDOM_SEED, d_n=res.d_n_labels)
             redo_front = False
+        lo, hi = res.bands[res.local[0]].own_lo, res.bands[res.local[-1]].own_hi
+        rows = hi - lo
+        seg_ptr = C.c_void_p(res.d_seg.data_ptr() + lo * W * 4)
+        # segm_soft = proba[slic] of the owned rows needs only the class probabilities: its gather and its (large) download run on
+        # a side stream while the main stream builds and cuts the graph
+        h_soft = soft_done = None
+        if want_soft:
+            side = eng.side_stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                d_soft = eng.buf('segm_soft', (rows, W, K), torch.float64)
+                _lib.check(lib.isb_gather(seg_ptr, C.c_longlong(rows * W), None, _lib.ptr(d_proba), K, None, _lib.ptr(d_soft),
+                                          _lib.stream_ptr()))
+                h_soft = eng.pinned_empty(d_soft.shape, d_soft.dtype)
+                h_soft.copy_(d_soft, non_blocking=True)
+                soft_done = torch.cuda.Event()
+                soft_done.record(side)
         cap = max(64, EDGE_CAP_PER_NODE[0] * nb)
         pairwise = compute_pairwise_cost(gc_regul, (nb, K))
         d_edges, d_n_edges, cap = eng.adjacency(res.d_seg, nb, cap)
         _, _, unary_i, edge_wi, smooth_i = eng.gc_energies(d_proba, d_edges, cap, d_n_edges, res.d_centres, _edge_mode(gc_edge_type), 1.0,
                                                            pairwise, d_n_nodes=res.d_n_labels)
         d_labels, _, _ = eng.alpha_expansion(nb, K, cap, d_n_edges, d_edges, edge_wi, unary_i, smooth_i, -1, d_n_nodes=res.d_n_labels)
-        # 5) LUT gathers of the owned rows
-        lo, hi = res.bands[res.local[0]].own_lo, res.bands[res.local[-1]].own_hi
-        rows = hi - lo
-        seg_ptr = C.c_void_p(res.d_seg.data_ptr() + lo * W * 4)
-        d_soft = eng.buf('segm_soft', (rows, W, K), torch.float64) if want_soft else None
+        # 5) LUT gather of the owned rows
         if gather_segm:
             d_full = eng.buf('segm', (H, W), torch.int32)
             d_segm = d_full[lo:hi]
         else:
             d_segm = eng.buf('segm', (rows, W), torch.int32)
-        _lib.check(lib.isb_gather(seg_ptr, C.c_longlong(rows * W), _lib.ptr(d_labels), _lib.ptr(d_proba) if want_soft else None, K,
-                                  _lib.ptr(d_segm), _lib.ptr(d_soft), st))
+        _lib.check(lib.isb_gather(seg_ptr, C.c_longlong(rows * W), _lib.ptr(d_labels), None, K, _lib.ptr(d_segm), None, st))
         if gather_segm and comm.world > 1:
             for r in range(comm.world):
                 blo = res.bands[r * bands_per_rank].own_lo
                 bhi = res.bands[(r + 1) * bands_per_rank - 1].own_hi
                 comm.broadcast(d_full[blo:bhi], r)
-        outs = [d_full if gather_segm else d_segm, d_n_edges, res.d_err] + ([d_soft] if want_soft else [])
+        outs = [d_full if gather_segm else d_segm, d_n_edges, res.d_err]
         host = []
         for t in outs:
             h = eng.pinned_empty(t.shape, t.dtype)
             h.copy_(t, non_blocking=True)
             host.append(h)
         torch.cuda.current_stream().synchronize()
+        if soft_done is not None:
+            soft_done.synchronize()
+        host.append(h_soft)
         if int(host[2][0]) != 0 and not force_whole:
             # orphan pixels beyond the halo (see slic_tiled): same answer on every rank, so every rank takes this branch
             logging.warning('banded SLIC met orphan pixels beyond the halo, redoing the sweeps on the whole image on every GPU')
