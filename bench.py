@@ -129,7 +129,7 @@ def load_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
-TRAFFIC_SOURCE = 'profiles/r01d_assign_traffic.json'
+TRAFFIC_SOURCE = 'profiles/r02c_assign_traffic.json'
 
 
 def load_traffic():
