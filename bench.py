@@ -267,7 +267,7 @@ def run_reference(args):
     # the reference's own rule is NB_WORKERS = 0.6 * cpu_count (pipelines.py:43); on the 128-CPU host of the B200 box the path
     # stops scaling at ~16 processes (measured r01: 1 -> 0.86, 8 -> 7.9, 16 -> 12.0, 32 -> 10.1, 64 -> 6.8 MPix/s; memory bound),
     # so 16 workers is the reference's best case and keeps a step at a few seconds
-    workers = min(16, max(1, int(0.6 * cores)))
+    workers = args.ref_workers or min(16, max(1, int(0.6 * cores)))
     n_img = workers  # one bounded sample per step: `workers` images through the process pool
     pool = ReferencePool(n_img, workers)
     for _ in range(args.warmup):
@@ -700,6 +700,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-images', type=int, default=4, help='images in the bounded cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ref-workers', type=int, default=0, help='processes of the reference arm (default: min(16, 0.6 * cpus), the measured best)')
     ap.add_argument('--workload', default='config2', choices=['config2', 'config3', 'config4', 'config5'],
                     help='config2 = the headline line (default); config5 = one 8192x8192 image banded over the GPUs (extra)')
     ap.add_argument('--tiled-side', type=int, default=8192)
