@@ -195,6 +195,9 @@ def test_segment_median_on_the_device(oracle):
         want = oracle.color2d_median(img, seg)
         assert np.isnan(got[17]).all()
         np.testing.assert_array_equal(np.delete(got, 17, 0), np.delete(want, 17, 0))
+    img3 = np.array([[[0] * 3 + [1] * 3 + [2] * 2] * 3] * 2, dtype=float)[:, :, :8]          # doctest volume of descriptors.py:698-715
+    seg3 = np.array([[[0] * 2 + [1] * 2 + [2] * 2 + [5] * 2] * 3] * 2)
+    np.testing.assert_allclose(ds.numpy_img3d_gray_median(img3, seg3)[[0, 1, 2, 5]], [0., 0.5, 1., 2.])
     vol = rng.random_sample((4, 20, 30))
     vseg = rng.randint(0, 9, vol.shape)
     want = np.array([np.median(vol[vseg == k]) for k in range(9)])
