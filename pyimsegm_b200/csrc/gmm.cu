@@ -798,20 +798,62 @@ __global__ void __launch_bounds__(1024) k_big_chol(int N_in, const int* n_dev, i
         else U[i] = 0.0;   // placeholder; the upper triangle is overwritten by Z^T below
     }
     __syncthreads();
-    // right-looking Cholesky, two barriers per column
-    for (int j = 0; j < D; ++j) {
-        const int jj = j * (j + 1) / 2 + j;
-        const double d = Ls[jj];              // final since the barrier that closed column j - 1; the same value in every thread
-        if (!(d > 0)) { if (tid == 0) s_bad = 1; break; }
-        const double piv = sqrt(d);
-        for (int i = j + 1 + tid; i < D; i += T) { const double v = Ls[i * (i + 1) / 2 + j] / piv; Ls[i * (i + 1) / 2 + j] = v; s_col[i] = v; }
+    // blocked right-looking Cholesky on the packed lower triangle, panels of PB columns, three block-wide barriers per PANEL:
+    //   (a) the PB x PB diagonal block, unblocked, by one warp (lane = row of the block, warp barriers only)
+    //   (b) the panel below it: every row solves its own small triangular system against the finished diagonal block
+    //   (c) the trailing matrix takes the rank-PB update, a warp per row with the row's panel entries in registers
+    constexpr int PB = 16;
+    auto idx = [](int i, int c) { return i * (i + 1) / 2 + c; };
+    for (int j0 = 0; j0 < D; j0 += PB) {
+        const int jb = min(PB, D - j0);
+        if (wid == 0) {
+            for (int jj = 0; jj < jb; ++jj) {
+                const int j = j0 + jj;
+                const double d = Ls[idx(j, j)];          // the same value in every lane
+                if (!(d > 0)) { if (lane == 0) s_bad = 1; break; }
+                const double piv = sqrt(d);
+                __syncwarp();
+                double lij = 0.0;
+                const bool below = lane > jj && lane < jb;
+                if (below) { lij = Ls[idx(j0 + lane, j)] / piv; Ls[idx(j0 + lane, j)] = lij; }
+                if (lane == jj) Ls[idx(j, j)] = piv;
+                __syncwarp();
+                if (below)
+                    for (int c = jj + 1; c <= lane; ++c) Ls[idx(j0 + lane, j0 + c)] = fma(-lij, Ls[idx(j0 + c, j)], Ls[idx(j0 + lane, j0 + c)]);
+                __syncwarp();
+            }
+        }
         __syncthreads();
-        if (tid == 0) Ls[jj] = piv;           // nobody reads the diagonal of a finished column before the loop ends
-        // trailing update L[i][c] -= L[i][j] L[c][j]: a warp per row i, lanes over c <= i, column j from shared memory
-        for (int i = j + 1 + wid; i < D; i += nw) {
-            const int ri = i * (i + 1) / 2;
-            const double li = s_col[i];
-            for (int c = j + 1 + lane; c <= i; c += 32) Ls[ri + c] = fma(-li, s_col[c], Ls[ri + c]);
+        if (s_bad) break;
+        for (int i = j0 + jb + tid; i < D; i += T) {
+            double x[PB];
+            const int ri = idx(i, j0);
+#pragma unroll
+            for (int c = 0; c < PB; ++c) {
+                if (c < jb) {
+                    double acc = Ls[ri + c];
+                    const int rc = idx(j0 + c, j0);
+#pragma unroll
+                    for (int pp = 0; pp < PB; ++pp) if (pp < c) acc = fma(-x[pp], Ls[rc + pp], acc);
+                    x[c] = acc / Ls[rc + c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < PB; ++c) if (c < jb) Ls[ri + c] = x[c];
+        }
+        __syncthreads();
+        for (int i = j0 + jb + wid; i < D; i += nw) {
+            const int ri = idx(i, 0);
+            double li[PB];
+#pragma unroll
+            for (int pp = 0; pp < PB; ++pp) li[pp] = pp < jb ? Ls[ri + j0 + pp] : 0.0;
+            for (int c = j0 + jb + lane; c <= i; c += 32) {
+                const int rc = idx(c, j0);
+                double acc = Ls[ri + c];
+#pragma unroll
+                for (int pp = 0; pp < PB; ++pp) if (pp < jb) acc = fma(-li[pp], Ls[rc + pp], acc);
+                Ls[ri + c] = acc;
+            }
         }
         __syncthreads();
     }
@@ -820,6 +862,9 @@ __global__ void __launch_bounds__(1024) k_big_chol(int N_in, const int* n_dev, i
         if (tid == 0) { w.state[init * 4 + 1] = 1.0; w.state[init * 4 + 3] = 1.0; } // done, failed
         return;
     }
+    // reciprocals of the diagonal (the forward substitution below multiplies instead of dividing 189 times per column)
+    for (int j = tid; j < D; j += T) s_col[j] = 1.0 / Ls[idx(j, j)];
+    __syncthreads();
     // Z = L^-1 (lower) by forward substitution, one warp per column c, the column in registers (lane l holds Z[c + l + 32 q][c]):
     //     Z[c][c] = 1 / L[c][c],   Z[r][c] = -(sum_{p=c}^{r-1} L[r][p] Z[p][c]) / L[r][r]   (r > c)
     // prec_chol = Z^T: column c of Z is row c of U.
@@ -828,7 +873,7 @@ __global__ void __launch_bounds__(1024) k_big_chol(int N_in, const int* n_dev, i
         double z[ZQ];
 #pragma unroll
         for (int q = 0; q < ZQ; ++q) z[q] = 0.0;
-        if (lane == 0) z[0] = 1.0 / Ls[c * (c + 1) / 2 + c];
+        if (lane == 0) z[0] = s_col[c];
         for (int r = c + 1; r < D; ++r) {
             const int rr = r * (r + 1) / 2;
             double sum = 0;
@@ -839,7 +884,7 @@ __global__ void __launch_bounds__(1024) k_big_chol(int N_in, const int* n_dev, i
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            const double val = -sum / Ls[rr + r];
+            const double val = -sum * s_col[r];
             const int owner = (r - c) & 31, slot = (r - c) >> 5;
 #pragma unroll
             for (int q = 0; q < ZQ; ++q) if (q == slot && lane == owner) z[q] = val;
@@ -865,10 +910,15 @@ __global__ void __launch_bounds__(1024) k_big_chol(int N_in, const int* n_dev, i
         }
     }
     __syncthreads();   // U complete (global memory, visible to the whole CTA)
-    for (int j = tid; j < D; j += T) {
+    // mu U: four lanes per column, each over a quarter of the rows
+    for (int j4 = tid; j4 < 4 * ((D + 7) / 8) * 8; j4 += T) {
+        const int j = j4 >> 2, part = j4 & 3;
         double a = 0;
-        for (int i = 0; i <= j; ++i) a = fma(mu[i], U[(size_t)i * D + j], a);
-        w.bvec[((size_t)init * K + k) * D + j] = a;
+        if (j < D)
+            for (int i = part; i <= j; i += 4) a = fma(mu[i], U[(size_t)i * D + j], a);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        if (j < D && part == 0) w.bvec[((size_t)init * K + k) * D + j] = a;
     }
     if (tid == 0) wts[k] = nk / N;
 }

@@ -448,8 +448,14 @@ __global__ void k_lm_finalize(int nb, int n_batt, int flags, const double* __res
 
 __global__ void k_lm_counts(const int* __restrict__ seg, size_t npx, int* counts)
 {
-    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < npx) atomicAdd(&counts[seg[p]], 1);
+    // neighbouring pixels mostly share a label: one atomic per (warp, label) instead of one per pixel
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = p < npx;
+    const unsigned act = __ballot_sync(0xffffffffu, in);
+    if (!in) return;
+    const int lb = seg[p];
+    const unsigned grp = __match_any_sync(act, lb);
+    if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&counts[lb], __popc(grp));
 }
 
 struct LmWs { double* p0; double* p1; double* p2; float* imgf; float* planes; double* S1; double* S2; double* G2; int* counts; };

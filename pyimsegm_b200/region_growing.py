@@ -540,7 +540,7 @@ def get_neighboring_candidates(slic_neighbours, labels, object_idx, use_other_ob
     """
     labels = np.asarray(labels)
     members = np.flatnonzero(labels == object_idx)
-    near = np.unique([n for m in members for n in slic_neighbours[m]]).astype(int)
+    near = np.unique(np.fromiter((n for m in members for n in slic_neighbours[m]), dtype=np.int64))
     if use_other_obj:
         return [int(n) for n in near if labels[n] != object_idx]
     return [int(n) for n in near if labels[n] == 0]
@@ -581,6 +581,7 @@ class _GrowingState(object):
         self.init_centres = _round_int(centres)
         _, self.edges = make_graph_segm_connect_grid2d_conn4(slic)
         self.neighbours = get_neighboring_segments(self.edges)
+        self.csr = _neighbours_csr(self.neighbours)
         self.shape_model, self.shape_type = shape_model, shape_type
         labels = np.zeros(len(self.points), dtype=int)
         self.lut_data_cost, self.labels = compute_data_costs_points(slic, slic_prob_fg, self.init_centres, labels)
@@ -656,44 +657,53 @@ def region_growing_shape_slic_greedy(slic, slic_prob_fg, centres, shape_model, s
     return state.labels
 
 
+def _neighbours_csr(slic_neighbours):
+    """list of neighbour lists -> (indptr, indices) arrays"""
+    counts = np.fromiter((len(n) for n in slic_neighbours), dtype=np.int64, count=len(slic_neighbours))
+    indptr = np.concatenate(([0], np.cumsum(counts)))
+    indices = np.fromiter((v for n in slic_neighbours for v in n), dtype=np.int64, count=int(indptr[-1]))
+    return indptr, indices
+
+
 def prepare_graphcut_variables(candidates, slic_points, slic_neighbours, slic_weights, labels, nb_centres, lut_data_cost, lut_shape_cost,
-                               coef_data, coef_shape, coef_pairwise, prob_label_trans):
+                               coef_data, coef_shape, coef_pairwise, prob_label_trans, _csr=None):
     """ the sub-graph of one growing step: the candidate superpixels (free, but only towards labels present among their neighbours)
-    plus their non-candidate neighbours (pinned to their current label) (reference region_growing.py:1391-1464)
+    plus their non-candidate neighbours (pinned to their current label) (reference region_growing.py:1391-1464; the reference grows
+    the vertex list and the unary table one neighbour at a time, here the whole band is assembled with array operations)
 
     :return tuple: vertexes (superpixel indices), edges [E, 2] (indices into vertexes), edge_weights, unary, pairwise
     """
     slic_points, labels = np.asarray(slic_points), np.asarray(labels)
-    if np.max(candidates) >= len(slic_points):
-        raise ValueError('max candidate idx: %d for %d centres' % (np.max(candidates), len(slic_points)))
-    max_neighbour = max(max(lb) for lb in slic_neighbours if lb)
-    if max_neighbour >= len(slic_points):
-        raise ValueError('max slic neighbours idx: %d for %d centres' % (max_neighbour, len(slic_points)))
+    cand = np.asarray(candidates, dtype=np.int64)
+    if np.max(cand) >= len(slic_points):
+        raise ValueError('max candidate idx: %d for %d centres' % (np.max(cand), len(slic_points)))
+    indptr, indices = _neighbours_csr(slic_neighbours) if _csr is None else _csr
+    if indices.size and indices.max() >= len(slic_points):
+        raise ValueError('max slic neighbours idx: %d for %d centres' % (indices.max(), len(slic_points)))
     nb_labels = nb_centres + 1
-    vertexes = list(candidates)
-    position = {}
-    for i, v in enumerate(vertexes):
-        position.setdefault(v, i)       # a superpixel listed twice keeps its first slot, as list.index finds it
-    unary_rows, edges = [], []
-    for i, idx in enumerate(candidates):
-        near_idx = slic_neighbours[idx]
-        cost = slic_weights[idx] * (coef_data * lut_data_cost[idx] + coef_shape * lut_shape_cost[idx])
-        absent = np.ones(nb_labels, dtype=bool)
-        absent[labels[near_idx]] = False
-        unary_rows.append(np.where(absent, GC_REPLACE_INF, cost))
-    pinned_rows = []
-    for i, idx in enumerate(candidates):
-        for n_idx in slic_neighbours[idx]:
-            if n_idx not in position:
-                position[n_idx] = len(vertexes)
-                vertexes.append(n_idx)
-                row = np.full(nb_labels, GC_REPLACE_INF)
-                row[labels[n_idx]] = 0
-                pinned_rows.append(row)
-            edges.append((i, position[n_idx]))
-    unary = np.array(unary_rows + pinned_rows).reshape(-1, nb_labels)
-    unary = np.maximum(unary, -np.log(MAX_UNARY_PROB))
-    edges = np.array(edges).reshape(-1, 2)
+    nc = len(cand)
+    # every (candidate slot, neighbour) pair, candidate by candidate, neighbours in list order
+    counts = indptr[cand + 1] - indptr[cand]
+    slot = np.repeat(np.arange(nc), counts)
+    offset = np.arange(int(counts.sum())) - np.repeat(np.cumsum(counts) - counts, counts)
+    nbr = indices[indptr[cand][slot] + offset]
+    # free vertices: the data + shape cost of the labels that occur among the neighbours, "infinite" otherwise
+    cost = np.asarray(slic_weights)[cand][:, None] * (coef_data * lut_data_cost[cand] + coef_shape * lut_shape_cost[cand])
+    present = np.zeros((nc, nb_labels), dtype=bool)
+    present[slot, labels[nbr]] = True
+    unary_free = np.where(present, cost, GC_REPLACE_INF)
+    # vertex numbering: candidates in list order (a repeated one keeps its first slot), then new neighbours as first met
+    position = np.full(len(slic_points), -1, dtype=np.int64)
+    position[cand[::-1]] = np.arange(nc)[::-1]
+    fresh = nbr[position[nbr] < 0]
+    _, first = np.unique(fresh, return_index=True)
+    pinned = fresh[np.sort(first)]
+    position[pinned] = nc + np.arange(len(pinned))
+    vertexes = cand.tolist() + pinned.tolist()
+    unary_pinned = np.full((len(pinned), nb_labels), GC_REPLACE_INF)
+    unary_pinned[np.arange(len(pinned)), labels[pinned]] = 0
+    unary = np.maximum(np.vstack([unary_free, unary_pinned]), -np.log(MAX_UNARY_PROB))
+    edges = np.stack([slot, position[nbr]], axis=1)
     edge_weights = np.ones(len(edges)) / compute_spatial_dist(slic_points[vertexes], edges, relative=True)
     pairwise = np.full((nb_labels, nb_labels), -np.log(prob_label_trans[0]))
     pairwise[1:, 1:] = -np.log(prob_label_trans[1])
@@ -733,7 +743,7 @@ def region_growing_shape_slic_graphcut(slic, slic_prob_fg, centres, shape_model,
     def cut_band(candidates, labels_gc):
         gc_vertexes, gc_edges, edge_weights, unary, pairwise = prepare_graphcut_variables(
             candidates, state.points, state.neighbours, state.weights, state.labels, len(state.centres), state.lut_data_cost,
-            state.lut_shape_cost, coef_data, coef_shape, coef_pairwise, prob_label_trans)
+            state.lut_shape_cost, coef_data, coef_shape, coef_pairwise, prob_label_trans, _csr=state.csr)
         if len(gc_edges) > 0:
             labels_gc[gc_vertexes] = cut_general_graph(gc_edges, edge_weights, unary, pairwise, n_iter=999)
 
