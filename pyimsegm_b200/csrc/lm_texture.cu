@@ -57,25 +57,36 @@ __global__ void __launch_bounds__(VB_T) k_lm_vblur(const double* __restrict__ in
         s_w[i] = (d >= -radius && d <= radius) ? wfull[d + radius] : 0.0;
     }
     __syncthreads();
-    const int x = blockIdx.x * VB_T + threadIdx.x;
+    // a thread owns TWO columns (x, x + VB_T) and VB_R consecutive output rows: every weight read from shared memory (a broadcast
+    // to the whole warp) feeds two FP64 FMAs, which balances the shared-memory pipe against the FP64 pipe
+    const int x = blockIdx.x * (2 * VB_T) + threadIdx.x, x2 = x + VB_T;
     const int y0 = blockIdx.y * VB_R;
     const size_t plane = (size_t)blockIdx.z * n0 * n1;
     if (x >= n1) return;
-    double acc[VB_R];
+    const bool two = x2 < n1;
+    double acc[2][VB_R];
 #pragma unroll
-    for (int r = 0; r < VB_R; ++r) acc[r] = 0.0;
+    for (int r = 0; r < VB_R; ++r) { acc[0][r] = 0.0; acc[1][r] = 0.0; }
     // input rows i = y0 - radius .. y0 + VB_R - 1 + radius; output row y0 + r uses weight w[i - (y0 + r)]
     const int i_beg = y0 - radius, i_end = y0 + VB_R - 1 + radius;
     const double* wc = s_w + (radius + VB_R); // wc[d]
     for (int i = i_beg; i <= i_end; ++i) {
-        const double v = in[plane + (size_t)reflect_idx(i, n0) * n1 + x];
+        const size_t row = plane + (size_t)reflect_idx(i, n0) * n1;
+        const double v0 = in[row + x], v1 = two ? in[row + x2] : 0.0;
         const int d0 = i - y0;
 #pragma unroll
-        for (int r = 0; r < VB_R; ++r) acc[r] = fma(wc[d0 - r], v, acc[r]);
+        for (int r = 0; r < VB_R; ++r) {
+            const double wgt = wc[d0 - r];
+            acc[0][r] = fma(wgt, v0, acc[0][r]);
+            acc[1][r] = fma(wgt, v1, acc[1][r]);
+        }
     }
 #pragma unroll
     for (int r = 0; r < VB_R; ++r)
-        if (y0 + r < n0) out[plane + (size_t)(y0 + r) * n1 + x] = acc[r];
+        if (y0 + r < n0) {
+            out[plane + (size_t)(y0 + r) * n1 + x] = acc[0][r];
+            if (two) out[plane + (size_t)(y0 + r) * n1 + x2] = acc[1][r];
+        }
 }
 
 // [planes][n0][n1] -> [planes][n1][n0]
@@ -530,12 +541,12 @@ extern "C" int isb_lm_texture(const void* img, int dtype, const int32_t* seg, in
         ISB_REQUIRE(smem <= 200 * 1024, "background radius too large");
         ISB_CUDA_CHECK(cudaFuncSetAttribute(k_lm_vblur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // axis 0 (rows): p0 [3][H][W] -> p1
-        k_lm_vblur<<<dim3((W + VB_T - 1) / VB_T, (H + VB_R - 1) / VB_R, 3), VB_T, smem, st>>>(w.p0, H, W, bg_weights, bg_radius, w.p1);
+        k_lm_vblur<<<dim3((W + 2 * VB_T - 1) / (2 * VB_T), (H + VB_R - 1) / VB_R, 3), VB_T, smem, st>>>(w.p0, H, W, bg_weights, bg_radius, w.p1);
         ISB_LAUNCH_CHECK();
         // axis 1 (cols): transpose, blur along the (new) rows axis; the result stays transposed [3][W][H]
         k_lm_transpose<<<dim3((W + 31) / 32, (H + 31) / 32, 3), 256, 0, st>>>(w.p1, H, W, w.p2);
         ISB_LAUNCH_CHECK();
-        k_lm_vblur<<<dim3((H + VB_T - 1) / VB_T, (W + VB_R - 1) / VB_R, 3), VB_T, smem, st>>>(w.p2, W, H, bg_weights, bg_radius, w.p1);
+        k_lm_vblur<<<dim3((H + 2 * VB_T - 1) / (2 * VB_T), (W + VB_R - 1) / VB_R, 3), VB_T, smem, st>>>(w.p2, W, H, bg_weights, bg_radius, w.p1);
         ISB_LAUNCH_CHECK();
     } else {
         ISB_CUDA_CHECK(cudaMemsetAsync(w.p1, 0, sizeof(double) * 3 * npx, st));

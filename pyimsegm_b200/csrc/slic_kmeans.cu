@@ -328,26 +328,43 @@ __global__ void __launch_bounds__(ATHREADS, 5) k_assign(const __grid_constant__ 
                 const double tx = __dsub_rn(cand[c].cx, xd);
                 const double dx2 = __dmul_rn(tx, tx);
                 bool improved = false;
+                // four rows at a time, straight-line code: the four spatial terms are independent chains (the FP64 latency of one
+                // hides behind the others), then -- only if one of the four can still win -- the four colour terms likewise
 #pragma unroll
-                for (int j = 0; j < AROWS; ++j) {
-                    const int y = yb + j + s.y_off;
-                    if ((unsigned)(y - cy0) >= cyn) continue;
-                    // (double)y without the conversion unit: y < 2^31 sits in the low mantissa word of 2^52 + y (exact)
-                    const double yd = __dsub_rn(__hiloint2double(0x43300000, y), 4503599627370496.0);
-                    const double ty = __dsub_rn(ccy, yd);
-                    const double sp = __dmul_rn(__dadd_rn(__dmul_rn(ty, ty), dx2), s.sw);
-                    // exact pruning: the colour term is >= 0 and fl(a + b) >= a for b >= 0, so d >= sp > best cannot win or tie.
-                    // (a NaN sp falls through: its NaN distance below never compares less than a minimum)
-                    if (sp > best[j]) continue;
-                    const int ry = warp * AROWS + j;
-                    const double d0 = __dsub_rn(s_px[0][ry][lane], cand[c].c0), d1 = __dsub_rn(s_px[1][ry][lane], cand[c].c1),
-                                 d2 = __dsub_rn(s_px[2][ry][lane], cand[c].c2);
-                    double dcol = __dmul_rn(d0, d0);
-                    dcol = __dadd_rn(dcol, __dmul_rn(d1, d1));
-                    dcol = __dadd_rn(dcol, __dmul_rn(d2, d2));
-                    const double dc = __dadd_rn(sp, SLICO ? __ddiv_rn(dcol, s_maxdc[c]) : dcol);
-                    // distances are >= +0 or NaN: the floating-point order is the order of the bit patterns, a NaN never wins
-                    if (dc < best[j] || (dc == best[j] && bestk[j] >= 0 && ck < bestk[j])) { best[j] = dc; bestk[j] = ck; improved = true; }
+                for (int jg = 0; jg < AROWS; jg += 4) {
+                    double sp[4];
+                    bool need[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int y = yb + jg + q + s.y_off;
+                        // (double)y without the conversion unit: y < 2^31 sits in the low mantissa word of 2^52 + y (exact)
+                        const double yd = __dsub_rn(__hiloint2double(0x43300000, y), 4503599627370496.0);
+                        const double ty = __dsub_rn(ccy, yd);
+                        sp[q] = __dmul_rn(__dadd_rn(__dmul_rn(ty, ty), dx2), s.sw);
+                        // inside the window, and exact pruning: the colour term is >= 0 and fl(a + b) >= a for b >= 0, so
+                        // d >= sp > best cannot win or tie (a NaN sp falls through: its NaN distance never compares less)
+                        need[q] = (unsigned)(y - cy0) < cyn && !(sp[q] > best[jg + q]);
+                    }
+                    if (!(need[0] | need[1] | need[2] | need[3])) continue;
+                    double dc[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int ry = warp * AROWS + jg + q;
+                        const double d0 = __dsub_rn(s_px[0][ry][lane], cand[c].c0), d1 = __dsub_rn(s_px[1][ry][lane], cand[c].c1),
+                                     d2 = __dsub_rn(s_px[2][ry][lane], cand[c].c2);
+                        double dcol = __dmul_rn(d0, d0);
+                        dcol = __dadd_rn(dcol, __dmul_rn(d1, d1));
+                        dcol = __dadd_rn(dcol, __dmul_rn(d2, d2));
+                        dc[q] = __dadd_rn(sp[q], SLICO ? __ddiv_rn(dcol, s_maxdc[c]) : dcol);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int j = jg + q;
+                        // distances are >= +0 or NaN: the floating-point order is the order of the bit patterns, a NaN never wins
+                        if (need[q] && (dc[q] < best[j] || (dc[q] == best[j] && bestk[j] >= 0 && ck < bestk[j]))) {
+                            best[j] = dc[q]; bestk[j] = ck; improved = true;
+                        }
+                    }
                 }
                 if (improved) {
                     worst = 0;
