@@ -461,7 +461,9 @@ __global__ void __launch_bounds__(GT) k_gmm_fit(int N_in, const int* n_dev, int 
 // FP64 throughout (the reference's scikit-learn model is float64); explicit fma() because the file is built with -fmad=false.
 // ---------------------------------------------------------------------------------------------------------------------
 
-constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int TM = 96, TN = 96, TK = 16;   // CTA tile of the FP64 GEMMs: 256 threads, a 6 x 6 register tile each
+constexpr int MT = TM / 16;                // (192 = 2 x 96 covers D = 189 with 3 % padding; six consecutive doubles per operand and k: three 16-byte loads)
+constexpr int GQ = TM * TK / 256;          // elements of one operand a thread stages per k-step
 
 // C[b] (M x Nn) = op(A[b]) B[b], row-major; TRANS_A: A[b] is stored Kd x M.  The sample count may come from the device (n_dev).
 // Batch b = (restart r, component k) = (b / per, b % per); operand X of the batch starts at X + r * strideXr + k * strideXk.
@@ -475,13 +477,13 @@ struct BatchStride { size_t ar, ak, br, bk, cr, ck, cs; };
 // b_upper: B[b] is upper triangular, so columns n0.. only need the rows below n0 + TN.
 struct FuseW { const double* sresp; const double* mu; size_t sr_r; int K; size_t mu_r; int D; };
 template <bool TRANS_A, bool FUSE_W>
-__global__ void __launch_bounds__(256) k_dgemm_batched(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+__global__ void __launch_bounds__(256, 2) k_dgemm_batched(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
                                                        double* __restrict__ C, int ldc, BatchStride bs, int M_in, int Nn, int Kd_in,
                                                        const int* n_dev, int n_is_m, const double* state, int per, int upper_only, int ksplit,
                                                        int b_upper, FuseW fw)
 {
-    __shared__ double As[TK][TM + 4];
-    __shared__ double Bs[TK][TN + 4];
+    __shared__ __align__(16) double As[TK][TM + 4];
+    __shared__ __align__(16) double Bs[TK][TN + 4];
     const int b = blockIdx.z / ksplit, split = blockIdx.z % ksplit, br = b / per, bk = b % per;
     if (state && state[(size_t)br * 4 + 1] != 0.0) return;
     if (upper_only && blockIdx.x < blockIdx.y) return;   // symmetric result: tiles below the diagonal are not needed
@@ -498,15 +500,15 @@ __global__ void __launch_bounds__(256) k_dgemm_batched(const double* __restrict_
     const double* sr = FUSE_W ? fw.sresp + br * fw.sr_r + bk : nullptr;          // sr[n * K]
     const double* mu = FUSE_W ? fw.mu + br * fw.mu_r + (size_t)bk * fw.D : nullptr;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double acc[4][4];
+    double acc[MT][MT];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    double ra[4], rb[4];
+        for (int j = 0; j < MT; ++j) acc[i][j] = 0.0;
+    double ra[GQ], rb[GQ];
     auto gload = [&](int k0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < GQ; ++q) {
             const int i = threadIdx.x + q * 256;
             int kk, mm;
             if (TRANS_A) { kk = i / TM; mm = i % TM; } else { mm = i / TK; kk = i % TK; }
@@ -525,7 +527,7 @@ __global__ void __launch_bounds__(256) k_dgemm_batched(const double* __restrict_
     if (k_begin < k_end) gload(k_begin);
     for (int k0 = k_begin; k0 < k_end; k0 += TK) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < GQ; ++q) {
             const int i = threadIdx.x + q * 256;
             if (TRANS_A) As[i / TM][i % TM] = ra[q]; else As[i % TK][i / TK] = ra[q];
             Bs[i / TN][i % TN] = rb[q];
@@ -534,23 +536,23 @@ __global__ void __launch_bounds__(256) k_dgemm_batched(const double* __restrict_
         if (k0 + TK < k_end) gload(k0 + TK);
 #pragma unroll
         for (int kk = 0; kk < TK; ++kk) {
-            double a[4], bb[4];
+            double a[MT], bb[MT];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; bb[i] = Bs[kk][tx * 4 + i]; }
+            for (int i = 0; i < MT; ++i) { a[i] = As[kk][ty * MT + i]; bb[i] = Bs[kk][tx * MT + i]; }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < MT; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+                for (int j = 0; j < MT; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int gm = m0 + ty * 4 + i;
+    for (int i = 0; i < MT; ++i) {
+        const int gm = m0 + ty * MT + i;
         if (gm >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gn = n0 + tx * 4 + j;
+        for (int j = 0; j < MT; ++j) {
+            const int gn = n0 + tx * MT + j;
             if (gn < Nn) C[(size_t)gm * ldc + gn] = acc[i][j];
         }
     }
