@@ -137,12 +137,12 @@ __global__ void __launch_bounds__(256) k_lm_mix_sub(const double* __restrict__ i
 // layout and used for every output row r with kernel row dy = s - r:  acc[r] += A_s * B_dy^T.
 // 3xTF32: image and weights are pre-split into a tf32 value and a tf32 remainder; acc += a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
 // (FP32 accumulate) keeps f32 accuracy -- the reference rounds every response to f32 before its statistics (descriptors.py:233).
-// Warp roles (320 threads):
+// Warp roles (448 threads):
 //   warp 0     TMA: the split weights of kernel row dy (one contiguous slice in operand layout, cp.async.bulk) into a 4-slot ring,
 //              and the source rows (2-D tensor-map loads of the reflect-padded hi / lo planes) into a 4-slot ring
 //   warp 1     allocates tensor memory; one lane issues every tcgen05.mma and the commits that free the rings
-//   warps 2-5  patch-matrix producers: raw row -> A_s (hi, lo), two stages
-//   warps 6-9  epilogue: tcgen05.ld the 3 x N accumulators of a pixel, max over the orientations of a battery, clip, then
+//   warps 2-9  patch-matrix producers: raw row -> A_s (hi, lo), two stages (two threads per pixel, half of the k chunks each)
+//   warps 10-13 epilogue: tcgen05.ld the 3 x N accumulators of a pixel, max over the orientations of a battery, clip, then
 //              run-length sums of r and r^2 along the row per (battery, output row) -> atomics on the per-superpixel sums.
 // Two accumulator buffers (2 x 3 x N <= 480 of the 512 tensor-memory columns): the epilogue of a tile overlaps the MMAs of the next.
 // The responses are never written to memory.
@@ -160,7 +160,8 @@ constexpr int NRAW = 4, NA = 2, NB = 4;   // ring depths: raw rows, patch matric
 constexpr int A_HALF = TM * KPAD * 4;     // bytes of one patch matrix (hi or lo)
 constexpr int A_STAGE = 2 * A_HALF;
 constexpr int A_LBO = (TM / 8) * 128;     // bytes between the two 16-byte K chunks of one MMA (K-major, no swizzle)
-constexpr int LM_THREADS = 320;
+constexpr int LM_PROD = 256;                // patch-matrix producer threads: two per pixel of the M tile, half of the k chunks each
+constexpr int LM_THREADS = 64 + LM_PROD + 128;
 
 struct LmTcArgs {
     const float* w_tc;   // [KW][hi|lo][KC][NPAD/8][8][4]: the weights of every kernel row in operand layout
@@ -224,8 +225,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_lm_conv_tc(const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NRAW; ++i) { mbar_init(raw_full(i), 1); mbar_init(raw_empty(i), TM); }
-        for (int i = 0; i < NA; ++i) { mbar_init(a_full(i), TM); mbar_init(a_empty(i), 1); }
+        for (int i = 0; i < NRAW; ++i) { mbar_init(raw_full(i), 1); mbar_init(raw_empty(i), LM_PROD); }
+        for (int i = 0; i < NA; ++i) { mbar_init(a_full(i), LM_PROD); mbar_init(a_empty(i), 1); }
         for (int i = 0; i < NB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), TM); }
         fence_mbar_init();
@@ -305,9 +306,9 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_lm_conv_tc(const __grid_const
                 jb_base += KW;
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 2 + LM_PROD / 32) {
         // ------------------------------------------------------------ patch-matrix producers ---------------------------------------
-        const int m = threadIdx.x - 64;
+        const int m = (threadIdx.x - 64) & (TM - 1), kh = (threadIdx.x - 64) >> 7;   // pixel of the tile, half of the k chunks
         uint32_t jr = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             for (int s = 0; s < SROWS; ++s, ++jr) {
@@ -319,7 +320,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_lm_conv_tc(const __grid_const
                 float4* dh = (float4*)(smem + Sm::OFF_A + st * A_STAGE) + (m >> 3) * 8 + (m & 7);
                 float4* dl = dh + A_HALF / 16;
 #pragma unroll
-                for (int k4 = 0; k4 < KC; ++k4) {
+                for (int q = 0; q < KC / 2; ++q) {
+                    const int k4 = kh * (KC / 2) + q;
                     dh[k4 * (A_LBO / 16)] = make_float4(rh[4 * k4], rh[4 * k4 + 1], rh[4 * k4 + 2], rh[4 * k4 + 3]);
                     dl[k4 * (A_LBO / 16)] = make_float4(rl[4 * k4], rl[4 * k4 + 1], rl[4 * k4 + 2], rl[4 * k4 + 3]);
                 }
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_lm_conv_tc(const __grid_const
         }
     } else {
         // ------------------------------------------------------------ epilogue ------------------------------------------------------
-        const int e = threadIdx.x - 192;          // 0..127
+        const int e = threadIdx.x - (64 + LM_PROD);   // 0..127
         const int q = warp & 3;                   // tensor-memory lane quarter this warp may read
         const int m = 32 * q + lane;
         float* T = (float*)(smem + Sm::OFF_T);

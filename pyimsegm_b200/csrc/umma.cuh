@@ -29,10 +29,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)   // suspend-time hint: the warp sleeps in hardware instead of spinning
         : "memory");
     return ok != 0;
 }
@@ -42,8 +42,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
+    unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
     }
 }
 
