@@ -285,11 +285,27 @@ size_t isb_lm_workspace_bytes(int H, int W, int nb, int n_batt);
 int isb_lm_texture(const void* img, int dtype, const int32_t* seg, int H, int W, int nb, const double* bg_weights, int bg_radius,
                    const double* chmix_host, const float* w_tc, int NP, int orient, int n_batt, int flags,
                    double* feat, int ld, int col0, void* ws, size_t ws_bytes, isb_stream_t stream);
+/* The same descriptor for ONE image cut into row bands over several GPUs ("one huge image"): every band runs
+ * isb_lm_texture_accumulate on its slab [slab_rows, W, 3] = the rows it owns, [y_first, y_end) in slab coordinates, plus a halo of
+ * bg_radius + 16 rows on every side that is not an image border (at a border the slab ends and reflects like the image); seg points
+ * at the slab's first row of the label map.  The sums of the owned rows are ADDED to acc (isb_lm_acc_doubles(nb, n_batt) doubles:
+ * sum r | sum r^2 | per-battery global sum r^2) and counts [nb] -- the caller zeroes them, sums them over the bands (all_reduce),
+ * and isb_lm_texture_finish forms the same features isb_lm_texture writes. */
+size_t isb_lm_acc_doubles(int nb, int n_batt);
+int isb_lm_texture_accumulate(const void* img, int dtype, const int32_t* seg, int slab_rows, int W, int y_first, int y_end, int nb,
+                              const double* bg_weights, int bg_radius, const double* chmix_host, const float* w_tc, int NP, int orient,
+                              int n_batt, double* acc, int32_t* counts, void* ws, size_t ws_bytes, isb_stream_t stream);
+int isb_lm_texture_finish(int nb, int n_batt, int flags, const double* acc, const int32_t* counts, double* feat, int ld, int col0,
+                          isb_stream_t stream);
 
 /* known-answer test of the tensor-core plumbing (tests/test_gpu_umma.py): D[128, N] = A[128, K] * B[N, K]^T with tcgen05.mma
  * kind::tf32 in one CTA; A, B row-major f32 holding tf32-representable values, N % 16 == 0 (<= 256), K % 8 == 0 (<= 64).
- * variant 0 = the descriptor convention the library uses; 1 = leading/stride byte offsets swapped (diagnostic only). */
+ * variant 0 = the descriptor convention the library uses; 1 = leading/stride byte offsets swapped (diagnostic only);
+ * 2 = A written into tensor memory with tcgen05.st and read from there by the instruction (the form the contraction uses). */
 int isb_umma_selftest(const float* A, const float* B, int N, int K, int variant, float* D, isb_stream_t stream);
+/* profiling aid: clocks that `reps` back-to-back tcgen05.mma kind::tf32 instructions (M 128, K 8, the given N) take on each of `ctas`
+ * CTAs; mode bit 0 = rotate over several accumulators, bit 1 = A operand from tensor memory.  cycles: device, [ctas] int64 */
+int isb_umma_rate(int N, int reps, int mode, int ctas, long long* cycles, isb_stream_t stream);
 
 /* per-segment, per-channel median -- numpy_img2d_color_median (imsegm/descriptors.py:420-455, channels = 3, n_px = H*W) and
  * numpy_img3d_gray_median (:651-676, channels = 1, n_px = D*H*W); np.median semantics (mean of the two middle values for an even

@@ -73,8 +73,12 @@ SIGNATURES = {
     'isb_gmm_params_len': (_i, [_i, _i]),
     'isb_gmm_fit_predict': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _d, _d, _i, C.c_ulonglong, _vp, _vp, _vp, _vp, _sz, _vp]),
     'isb_lm_workspace_bytes': (_sz, [_i, _i, _i, _i]),
+    'isb_lm_acc_doubles': (_sz, [_i, _i]),
+    'isb_lm_texture_accumulate': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, C.POINTER(_d), _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    'isb_lm_texture_finish': (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     'isb_lm_texture': (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, C.POINTER(_d), _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _sz, _vp]),
     'isb_umma_selftest': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    'isb_umma_rate': (_i, [_i, _i, _i, _i, _vp, _vp]),
     'isb_fill_i32': (_i, [_vp, _ll, _i, _vp]),
     'isb_combine': (_i, [_vp, _vp, _ll, _i, _vp]),
     'isb_gray_stats_workspace_bytes': (_sz, [_i]),

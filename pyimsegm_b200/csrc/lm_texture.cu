@@ -21,6 +21,8 @@
 // Tolerance against the float64 oracle: 2e-4 relative on the features (stated in tests/test_gpu_texture.py).
 #include "common.cuh"
 #include "umma.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -167,6 +169,7 @@ struct LmTcArgs {
     const float* w_tc;   // [KW][hi|lo][KC][NPAD/8][8][4]: the weights of every kernel row in operand layout
     const int* seg;      // [H][W]
     int H, W, tiles_x, tiles_y, Hp;
+    int y_first, y_end;  // rows [y_first, y_end) of the slab are this call's: tiles start at y_first, rows >= y_end are masked
     int n_batt;
     double* S1;          // [nb][n_batt*3] sum r
     double* S2;          // [nb][n_batt*3] sum r^2
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_lm_conv_tc(const __grid_const
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const int ch = t / tiles_per_ch, rem = t - ch * tiles_per_ch;
                 const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-                const int x0 = tx * TM, y0 = ty * TR;
+                const int x0 = tx * TM, y0 = a.y_first + ty * TR;
                 for (int s = 0; s < SROWS; ++s) {
                     if (s < KW) {
                         const uint32_t slot = jb % NB, ph = (jb / NB) & 1;
@@ -345,12 +348,12 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_lm_conv_tc(const __grid_const
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const int ch = t / tiles_per_ch, rem = t - ch * tiles_per_ch;
             const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-            const int x0 = tx * TM, y0 = ty * TR;
+            const int x0 = tx * TM, y0 = a.y_first + ty * TR;
             const uint32_t buf = it & 1;
 #pragma unroll
             for (int r = 0; r < TR; ++r) {
                 const int y = y0 + r, x = x0 + m;
-                s_lab[r * TM + m] = (y < a.H && x < a.W) ? a.seg[(size_t)y * a.W + x] : -1;
+                s_lab[r * TM + m] = (y < a.y_end && x < a.W) ? a.seg[(size_t)y * a.W + x] : -1;
             }
             mbar_wait(acc_full(buf), (it >> 1) & 1);
             tc_fence_after();
@@ -375,6 +378,271 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_lm_conv_tc(const __grid_const
             }
             tc_fence_before();
             mbar_arrive(acc_empty(buf));                                    // the tile after next may overwrite this accumulator buffer
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (walker) {
+                // one (output row, battery) pair and half a row per thread: run-length sums along x, flushed when the label changes
+                const size_t fstride = (size_t)a.n_batt * 3;
+                double s1 = 0.0, s2 = 0.0;
+                int cur = -1;
+                const int* lab = s_lab + wr * TM + half * (TM / 2);
+                const float* tv = T + (size_t)(wr * TM + half * (TM / 2)) * Sm::TS + wb;
+                for (int i = 0; i < TM / 2; ++i) {
+                    const int lb = lab[i];
+                    if (lb != cur) {
+                        if (cur >= 0) {
+                            atomicAdd(&a.S1[(size_t)cur * fstride + wb * 3 + ch], s1);
+                            atomicAdd(&a.S2[(size_t)cur * fstride + wb * 3 + ch], s2);
+                            g2 += s2;
+                        }
+                        cur = lb; s1 = 0.0; s2 = 0.0;
+                    }
+                    if (lb >= 0) { const double v = (double)tv[(size_t)i * Sm::TS]; s1 += v; s2 += v * v; }
+                }
+                if (cur >= 0) {
+                    atomicAdd(&a.S1[(size_t)cur * fstride + wb * 3 + ch], s1);
+                    atomicAdd(&a.S2[(size_t)cur * fstride + wb * 3 + ch], s2);
+                    g2 += s2;
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        if (walker && g2 != 0.0) atomicAdd(&a.G2[wb], g2);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tbase, 512);
+}
+
+// ---- the same contraction, re-cut for what the tensor core actually charges ---------------------------------------------------------
+// Measured on B200 (scripts/dev_umma_rate.py, profiles/r02_umma_rate.md): a tcgen05.mma kind::tf32 of M 128 x K 8 costs
+//   max(~104, N/2 + 43) clocks with A in shared memory,  max(~104, N/2 + 10) clocks with A in tensor memory
+// -- a floor of ~104 clocks per instruction whatever N is.  The first tcgen05 version above issues N = 80 instructions (ideal 40
+// clocks) and sits on that floor: 1485 instructions per tile, tensor pipe 57 % busy.  This version
+//   * keeps the patch matrices A_s (value and remainder, 2 x 40 columns, lane = pixel) in TENSOR MEMORY: the producers write them
+//     with tcgen05.st, the instruction reads only the weights from shared memory;
+//   * runs the three output rows of a tile as ONE instruction of N = 3 x NPAD: A_s is the same for them, their accumulators are
+//     adjacent tensor-memory columns, and the three weight slices (kernel rows s-2, s-1, s) are adjacent in shared memory because the
+//     weight ring is laid out per 16-byte k-chunk ([half][k-chunk][slot][NPAD/8 groups][8 x 16 B]; the first two slots are mirrored
+//     behind the last so that a window of three never wraps).  525 instructions per tile instead of 1485, 130 clocks each at N = 240.
+// Tensor-memory budget (512 columns): the accumulators of one tile (3 x 80 = 240; the short bank has room for two tiles) + a ring of
+// patch-matrix stages of 80 columns.
+template <int NPAD> struct LmTs {
+    using Bk = LmBank<NPAD>;
+    static constexpr int NACC = (2 * TR * NPAD + 2 * 2 * KPAD <= 512) ? 2 : 1;       // accumulator buffers
+    static constexpr int A_COL0 = (NACC * TR * NPAD + 31) / 32 * 32;                 // first patch-matrix column
+    static constexpr int NAT = (512 - A_COL0) / (2 * KPAD) > 3 ? 3 : (512 - A_COL0) / (2 * KPAD);   // patch-matrix stages
+    static constexpr int NBT = NPAD == 80 ? 5 : 8;                                   // weight slices in flight (logical ring)
+    static constexpr int PHYS = NBT + TR - 1;                                        // physical slots: the first TR-1 are mirrored at the end
+    static constexpr int SLOTC = (NPAD / 8) * 128;                                   // bytes of one (slice, half, k-chunk): NPAD filters x 4 taps
+    static constexpr int B_LBO = PHYS * SLOTC;                                       // bytes between the two k-chunks of an instruction
+    static constexpr int B_HALF = KC * B_LBO;                                        // bytes of the value (or remainder) ring
+    static constexpr int B_SLICE = 2 * KC * SLOTC;                                   // bytes of one weight slice (value + remainder)
+    static constexpr int TS = Bk::NBATT + 1;
+    static constexpr int OFF_B = 0;
+    static constexpr int OFF_RAW = OFF_B + 2 * B_HALF;
+    static constexpr int OFF_T = OFF_RAW + NRAW * 2 * RAW_PITCH;
+    static constexpr int OFF_LAB = OFF_T + TR * TM * TS * 4;
+    static constexpr int OFF_BAR = OFF_LAB + TR * TM * 4;
+    static constexpr int N_BAR = 2 * NRAW + 2 * NAT + 2 * NBT + 2 * NACC;
+    static constexpr int OFF_TMEM = OFF_BAR + N_BAR * 8;
+    static constexpr int BYTES = OFF_TMEM + 16;
+    static_assert(NAT >= 2, "tensor memory budget: at least two patch-matrix stages");
+    static_assert(A_COL0 + NAT * 2 * KPAD <= 512, "tensor memory budget");
+    static_assert(NBT >= TR + 1, "the weight ring must hold a window of TR slices and one in flight");
+    static_assert(TR * NPAD <= 256, "one instruction spans the accumulators of all output rows");
+    static_assert(BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <int NPAD>
+__global__ void __launch_bounds__(LM_THREADS, 1) k_lm_conv_ts(const __grid_constant__ CUtensorMap tmap, LmTcArgs a)
+{
+    using namespace umma;
+    using Sm = LmTs<NPAD>;
+    using Bk = LmBank<NPAD>;
+    constexpr int NAT = Sm::NAT, NBT = Sm::NBT, NACC = Sm::NACC;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar0 = sbase + Sm::OFF_BAR;
+    auto raw_full = [&](uint32_t i) { return bar0 + 8u * i; };
+    auto raw_empty = [&](uint32_t i) { return bar0 + 8u * (NRAW + i); };
+    auto a_full = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + i); };
+    auto a_empty = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + NAT + i); };
+    auto b_full = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + 2 * NAT + i); };
+    auto b_empty = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + 2 * NAT + NBT + i); };
+    auto acc_full = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + 2 * NAT + 2 * NBT + i); };
+    auto acc_empty = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + 2 * NAT + 2 * NBT + NACC + i); };
+    uint32_t* tmem_slot = (uint32_t*)(smem + Sm::OFF_TMEM);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NRAW; ++i) { mbar_init(raw_full(i), 1); mbar_init(raw_empty(i), LM_PROD / 32); }
+        for (int i = 0; i < NAT; ++i) { mbar_init(a_full(i), LM_PROD / 32); mbar_init(a_empty(i), 1); }
+        for (int i = 0; i < NBT; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+        for (int i = 0; i < NACC; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), TM); }
+        fence_mbar_init();
+        prefetch_tmap(&tmap);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tmem_slot;
+
+    const int tiles_per_ch = a.tiles_x * a.tiles_y;
+    const int n_tiles = 3 * tiles_per_ch;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer ------------------------------------------------
+        if (lane == 0) {
+            uint32_t jr = 0, jb = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int ch = t / tiles_per_ch, rem = t - ch * tiles_per_ch;
+                const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+                const int x0 = tx * TM, y0 = a.y_first + ty * TR;
+                for (int s = 0; s < SROWS; ++s) {
+                    if (s < KW) {
+                        // kernel row s: 2 x KC pieces of NPAD filters x 4 taps, each to its k-chunk's ring (and to the mirror slot)
+                        const uint32_t slot = jb % NBT, ph = (jb / NBT) & 1;
+                        const bool mirror = slot < TR - 1;
+                        mbar_wait(b_empty(slot), ph ^ 1);
+                        mbar_arrive_expect_tx(b_full(slot), (mirror ? 2 : 1) * Sm::B_SLICE);
+                        const float* src = a.w_tc + (size_t)s * (Sm::B_SLICE / 4);
+#pragma unroll 1
+                        for (int c = 0; c < 2 * KC; ++c) {
+                            const uint32_t dst = sbase + Sm::OFF_B + (uint32_t)c * Sm::B_LBO + slot * Sm::SLOTC;
+                            bulk_g2s(dst, src + (size_t)c * (Sm::SLOTC / 4), Sm::SLOTC, b_full(slot));
+                            if (mirror) bulk_g2s(dst + NBT * Sm::SLOTC, src + (size_t)c * (Sm::SLOTC / 4), Sm::SLOTC, b_full(slot));
+                        }
+                        ++jb;
+                    }
+                    const uint32_t slot = jr % NRAW, ph = (jr / NRAW) & 1;
+                    mbar_wait(raw_empty(slot), ph ^ 1);
+                    mbar_arrive_expect_tx(raw_full(slot), 2 * RAWW * 4);
+                    const uint32_t dst = sbase + Sm::OFF_RAW + slot * 2 * RAW_PITCH;
+                    tma_load_2d(dst, &tmap, x0, ch * a.Hp + y0 + s, raw_full(slot));
+                    tma_load_2d(dst + RAW_PITCH, &tmap, x0, (3 + ch) * a.Hp + y0 + s, raw_full(slot));
+                    ++jr;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer --------------------------------------------------
+        if (lane == 0) {
+            uint32_t jr = 0, jb_base = 0, it = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+                const uint32_t buf = it % NACC;
+                mbar_wait(acc_empty(buf), ((it / NACC) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t acc0 = tbase + buf * (TR * NPAD);
+                for (int s = 0; s < SROWS; ++s) {
+                    const uint32_t st = jr % NAT;
+                    if (s < KW) { const uint32_t jb = jb_base + s; mbar_wait(b_full(jb % NBT), (jb / NBT) & 1); }
+                    mbar_wait(a_full(st), (jr / NAT) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = tbase + Sm::A_COL0 + st * (2 * KPAD), a_lo = a_hi + KPAD;
+                    // output rows r_lo..r_hi take this source row with kernel rows dy = s - r; ascending dy = ascending slot = descending r,
+                    // and the accumulator of row r sits at column (TR-1-r) NPAD, so one instruction of N = nr NPAD covers them all
+                    const int r_hi = s < TR ? s : TR - 1, r_lo = s >= KW ? s - (KW - 1) : 0;
+                    const int nr = r_hi - r_lo + 1;
+                    const uint32_t b0 = sbase + Sm::OFF_B + ((jb_base + s - r_hi) % NBT) * Sm::SLOTC;    // slice dy = s - r_hi, value ring
+                    const uint32_t d0 = acc0 + (TR - 1 - r_hi) * NPAD;
+                    const uint32_t idesc = instr_desc(FMT_TF32, TM, nr * NPAD);
+                    // row r_hi = s < TR meets its accumulator for the first time (dy = 0): its very first instruction overwrites, alone
+                    const bool fresh = s < TR;
+#pragma unroll
+                    for (int kk = 0; kk < KPAD / 8; ++kk) {
+                        const uint64_t bh = smem_desc(b0 + kk * 2 * Sm::B_LBO, Sm::B_LBO, 128);
+                        const uint64_t bl = smem_desc(b0 + Sm::B_HALF + kk * 2 * Sm::B_LBO, Sm::B_LBO, 128);
+                        if (kk == 0 && fresh) {
+                            mma_tf32_ts(d0, a_lo, bh, instr_desc(FMT_TF32, TM, NPAD), 0u);
+                            if (nr > 1)
+                                mma_tf32_ts(d0 + NPAD, a_lo, smem_desc(b0 + Sm::SLOTC, Sm::B_LBO, 128), instr_desc(FMT_TF32, TM, (nr - 1) * NPAD), 1u);
+                        } else {
+                            mma_tf32_ts(d0, a_lo + kk * 8, bh, idesc, 1u);                    // small terms first
+                        }
+                        mma_tf32_ts(d0, a_hi + kk * 8, bl, idesc, 1u);
+                        mma_tf32_ts(d0, a_hi + kk * 8, bh, idesc, 1u);
+                    }
+                    tc_commit(a_empty(st));                                              // the patch matrices of row s are free again
+                    if (s >= TR - 1) tc_commit(b_empty((jb_base + s - (TR - 1)) % NBT)); // kernel row s - (TR-1) had its last use
+                    ++jr;
+                }
+                tc_commit(acc_full(buf));
+                jb_base += KW;
+            }
+        }
+    } else if (warp < 2 + LM_PROD / 32) {
+        // ------------------------------------------------------------ patch-matrix producers ---------------------------------------
+        // a warp may touch the tensor-memory lanes 32 (warp % 4) .. +31: pixel m = that lane; of the two warps that share a lane quarter
+        // one writes the tf32 values, the other the remainders
+        const int q = warp & 3, m = 32 * q + lane, part = (warp - 2) >> 2;
+        uint32_t jr = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int s = 0; s < SROWS; ++s, ++jr) {
+                const uint32_t rs = jr % NRAW, st = jr % NAT;
+                mbar_wait(raw_full(rs), (jr / NRAW) & 1);
+                mbar_wait(a_empty(st), ((jr / NAT) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t* src = (const uint32_t*)(smem + Sm::OFF_RAW + rs * 2 * RAW_PITCH + part * RAW_PITCH) + m;
+                const uint32_t dst = tbase + ((uint32_t)(32 * q) << 16) + Sm::A_COL0 + st * (2 * KPAD) + part * KPAD;
+#pragma unroll
+                for (int kk = 0; kk < KPAD / 8; ++kk) {
+                    uint32_t r[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] = src[8 * kk + j];
+                    tmem_st8(dst + 8 * kk, r);
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(a_full(st)); mbar_arrive(raw_empty(rs)); }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue ------------------------------------------------------
+        const int e = threadIdx.x - (64 + LM_PROD);   // 0..127
+        const int q = warp & 3;                   // tensor-memory lane quarter this warp may read
+        const int m = 32 * q + lane;
+        float* T = (float*)(smem + Sm::OFF_T);
+        int* s_lab = (int*)(smem + Sm::OFF_LAB);
+        const bool walker = e < 2 * TR * Bk::NBATT;
+        const int p = e >> 1, half = e & 1;
+        const int wr = p / Bk::NBATT, wb = p - wr * Bk::NBATT;
+        double g2 = 0.0;
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const int ch = t / tiles_per_ch, rem = t - ch * tiles_per_ch;
+            const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+            const int x0 = tx * TM, y0 = a.y_first + ty * TR;
+            const uint32_t buf = it % NACC;
+#pragma unroll
+            for (int r = 0; r < TR; ++r) {
+                const int y = y0 + r, x = x0 + m;
+                s_lab[r * TM + m] = (y < a.y_end && x < a.W) ? a.seg[(size_t)y * a.W + x] : -1;
+            }
+            mbar_wait(acc_full(buf), (it / NACC) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int r = 0; r < TR; ++r) {
+                float bat[Bk::NBATT];
+#pragma unroll
+                for (int b = 0; b < Bk::NBATT; ++b) bat[b] = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < NPAD / 16; ++c) {
+                    if (16 * c >= Bk::GS * Bk::NG + Bk::NS) continue;       // padding columns only
+                    float v[16];
+                    tmem_ld16(tbase + ((uint32_t)(32 * q) << 16) + buf * (TR * NPAD) + (TR - 1 - r) * NPAD + 16 * c, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int b = lm_batt_of_col<NPAD>(16 * c + j);
+                        if (b >= 0) bat[b] = fmaxf(bat[b], v[j]);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < Bk::NBATT; ++b) T[(r * TM + m) * Sm::TS + b] = fminf(bat[b], 1.e6f);   // MAX_SIGNAL_RESPONSE
+            }
+            tc_fence_before();
+            mbar_arrive(acc_empty(buf));                                    // the accumulators are in shared memory: the next tile may start
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (walker) {
                 // one (output row, battery) pair and half a row per thread: run-length sums along x, flushed when the label changes
@@ -471,15 +739,18 @@ __global__ void k_lm_counts(const int* __restrict__ seg, size_t npx, int* counts
     if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&counts[lb], __popc(grp));
 }
 
-struct LmWs { double* p0; double* p1; double* p2; float* imgf; float* planes; double* S1; double* S2; double* G2; int* counts; };
+struct LmWs { double* p0; double* p1; double* p2; float* imgf; float* planes; double* acc; int* counts; };
 
-struct LmDims { int tiles_x, tiles_y, Hp, Wp; };
+// accumulators of one image: S1 [nb][n_batt*3] | S2 [nb][n_batt*3] | G2 [32], one block so that the banded path sums it with one all_reduce
+static size_t lm_acc_doubles(int nb, int n_batt) { return 2 * (size_t)nb * n_batt * 3 + 32; }
+
+struct LmDims { int tiles_x, Hp, Wp; };
 static LmDims lm_dims(int H, int W)
 {
     LmDims d;
-    d.tiles_x = (W + TM - 1) / TM; d.tiles_y = (H + TR - 1) / TR;
-    d.Hp = d.tiles_y * TR + KW - 1;        // every source row a tile asks for exists (rows past the image are reflections too)
-    d.Wp = d.tiles_x * TM + KPAD;          // a multiple of 4 floats: tensor-map row pitch is a multiple of 16 bytes
+    d.tiles_x = (W + TM - 1) / TM;
+    d.Hp = ((H + TR - 1) / TR + 1) * TR + KW - 1;   // every source row a tile asks for exists, wherever the first tile row starts
+    d.Wp = d.tiles_x * TM + KPAD;                   // a multiple of 4 floats: tensor-map row pitch is a multiple of 16 bytes
     return d;
 }
 
@@ -491,10 +762,17 @@ static size_t carve_lm(LmWs& w, void* ws, size_t bytes, int H, int W, int nb, in
     w.p0 = c.take<double>(n); w.p1 = c.take<double>(n); w.p2 = c.take<double>(n);
     w.imgf = c.take<float>(n);
     w.planes = c.take<float>(6 * (size_t)d.Hp * d.Wp);
-    w.S1 = c.take<double>((size_t)nb * n_batt * 3); w.S2 = c.take<double>((size_t)nb * n_batt * 3);
-    w.G2 = c.take<double>(32);
+    w.acc = c.take<double>(lm_acc_doubles(nb, n_batt));
     w.counts = c.take<int>(nb);
     return isb_align(c.off);
+}
+
+// ISB_LM_OPERANDS=smem keeps both operands of the contraction in shared memory (the first tcgen05 version, kept for A/B timing)
+static bool lm_a_in_tmem()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ISB_LM_OPERANDS"); v = (e && !strcmp(e, "smem")) ? 0 : 1; }
+    return v == 1;
 }
 
 template <int NPAD>
@@ -503,36 +781,23 @@ static int launch_lm_conv(const CUtensorMap& tmap, const LmTcArgs& a, int n_tile
     int dev = 0, sms = 0;
     ISB_CUDA_CHECK(cudaGetDevice(&dev));
     ISB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    ISB_CUDA_CHECK(cudaFuncSetAttribute(k_lm_conv_tc<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmSmem<NPAD>::BYTES));
     const int grid = n_tiles < sms ? n_tiles : sms;   // persistent: one CTA per SM, tiles round-robin
-    k_lm_conv_tc<NPAD><<<grid, LM_THREADS, LmSmem<NPAD>::BYTES, st>>>(tmap, a);
+    if (lm_a_in_tmem()) {
+        ISB_CUDA_CHECK(cudaFuncSetAttribute(k_lm_conv_ts<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmTs<NPAD>::BYTES));
+        k_lm_conv_ts<NPAD><<<grid, LM_THREADS, LmTs<NPAD>::BYTES, st>>>(tmap, a);
+    } else {
+        ISB_CUDA_CHECK(cudaFuncSetAttribute(k_lm_conv_tc<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmSmem<NPAD>::BYTES));
+        k_lm_conv_tc<NPAD><<<grid, LM_THREADS, LmSmem<NPAD>::BYTES, st>>>(tmap, a);
+    }
     ISB_LAUNCH_CHECK();
     return ISB_OK;
 }
 
-} // namespace
-
-extern "C" size_t isb_lm_workspace_bytes(int H, int W, int nb, int n_batt)
+// background subtraction + contraction over the slab img [H][W][3]; the sums of the rows [y_first, y_end) are ADDED to acc / counts
+static int lm_accumulate(const void* img, int dtype, const int32_t* seg, int H, int W, int y_first, int y_end, int nb, const double* bg_weights,
+                         int bg_radius, const double* chmix_host, const float* w_tc, int orient, int n_batt, const LmWs& w, double* acc,
+                         int* counts, cudaStream_t st)
 {
-    LmWs w;
-    return carve_lm(w, nullptr, 0, H, W, nb, n_batt);
-}
-
-extern "C" int isb_lm_texture(const void* img, int dtype, const int32_t* seg, int H, int W, int nb, const double* bg_weights, int bg_radius,
-                              const double* chmix_host, const float* w_tc, int NP, int orient, int n_batt, int flags,
-                              double* feat, int ld, int col0, void* ws, size_t ws_bytes, isb_stream_t stream)
-{
-    ISB_REQUIRE(img && seg && w_tc && feat && ws && chmix_host, "null pointer");
-    ISB_REQUIRE(H > 0 && W > 0 && nb > 0, "bad sizes");
-    ISB_REQUIRE(dtype >= ISB_U8 && dtype <= ISB_F64, "bad dtype");
-    ISB_REQUIRE((orient == 8 && NP == 80 && n_batt == 20) || (orient == 4 && NP == 48 && n_batt == 15),
-                "filter bank layout must be the full (8 orientations, 80 padded filters, 20 batteries) or the short one (4, 48, 15)");
-    ISB_REQUIRE(bg_radius >= 0 && (bg_radius == 0 || bg_weights), "background weights missing");
-    LmWs w;
-    size_t need = carve_lm(w, ws, ws_bytes, H, W, nb, n_batt);
-    ISB_REQUIRE(need <= ws_bytes, "workspace too small");
-    cudaStream_t st = (cudaStream_t)stream;
-    ProfScope prof(ISB_PROF_LM, st);
     const size_t npx = (size_t)H * W;
     k_lm_to_planar<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(img, dtype, npx, w.p0);
     ISB_LAUNCH_CHECK();
@@ -572,18 +837,86 @@ extern "C" int isb_lm_texture(const void* img, int dtype, const int32_t* seg, in
                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { isb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return ISB_ERR_CUDA; }
     }
-    ISB_CUDA_CHECK(cudaMemsetAsync(w.S1, 0, sizeof(double) * (size_t)nb * n_batt * 3, st));
-    ISB_CUDA_CHECK(cudaMemsetAsync(w.S2, 0, sizeof(double) * (size_t)nb * n_batt * 3, st));
-    ISB_CUDA_CHECK(cudaMemsetAsync(w.G2, 0, sizeof(double) * 32, st));
-    ISB_CUDA_CHECK(cudaMemsetAsync(w.counts, 0, sizeof(int) * (size_t)nb, st));
-    k_lm_counts<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(seg, npx, w.counts);
+    const size_t nown = (size_t)(y_end - y_first) * W;
+    k_lm_counts<<<(unsigned)((nown + 255) / 256), 256, 0, st>>>(seg + (size_t)y_first * W, nown, counts);
     ISB_LAUNCH_CHECK();
     LmTcArgs a;
-    a.w_tc = w_tc; a.seg = seg; a.H = H; a.W = W; a.tiles_x = d.tiles_x; a.tiles_y = d.tiles_y; a.Hp = d.Hp; a.n_batt = n_batt;
-    a.S1 = w.S1; a.S2 = w.S2; a.G2 = w.G2;
-    const int n_tiles = 3 * d.tiles_x * d.tiles_y;
-    if (int rc = (orient == 8 ? launch_lm_conv<80>(tmap, a, n_tiles, st) : launch_lm_conv<48>(tmap, a, n_tiles, st))) return rc;
-    k_lm_finalize<<<(nb * n_batt + 255) / 256, 256, 0, st>>>(nb, n_batt, flags, w.S1, w.S2, w.G2, w.counts, feat, ld, col0);
+    a.w_tc = w_tc; a.seg = seg; a.H = H; a.W = W; a.tiles_x = d.tiles_x; a.tiles_y = (y_end - y_first + TR - 1) / TR; a.Hp = d.Hp; a.n_batt = n_batt;
+    a.y_first = y_first; a.y_end = y_end;
+    a.S1 = acc; a.S2 = acc + (size_t)nb * n_batt * 3; a.G2 = acc + 2 * (size_t)nb * n_batt * 3;
+    const int n_tiles = 3 * a.tiles_x * a.tiles_y;
+    return orient == 8 ? launch_lm_conv<80>(tmap, a, n_tiles, st) : launch_lm_conv<48>(tmap, a, n_tiles, st);
+}
+
+static bool lm_bank_ok(int NP, int orient, int n_batt)
+{
+    return (orient == 8 && NP == 80 && n_batt == 20) || (orient == 4 && NP == 48 && n_batt == 15);
+}
+
+} // namespace
+
+extern "C" size_t isb_lm_workspace_bytes(int H, int W, int nb, int n_batt)
+{
+    LmWs w;
+    return carve_lm(w, nullptr, 0, H, W, nb, n_batt);
+}
+
+extern "C" size_t isb_lm_acc_doubles(int nb, int n_batt) { return lm_acc_doubles(nb, n_batt); }
+
+extern "C" int isb_lm_texture(const void* img, int dtype, const int32_t* seg, int H, int W, int nb, const double* bg_weights, int bg_radius,
+                              const double* chmix_host, const float* w_tc, int NP, int orient, int n_batt, int flags,
+                              double* feat, int ld, int col0, void* ws, size_t ws_bytes, isb_stream_t stream)
+{
+    ISB_REQUIRE(img && seg && w_tc && feat && ws && chmix_host, "null pointer");
+    ISB_REQUIRE(H > 0 && W > 0 && nb > 0, "bad sizes");
+    ISB_REQUIRE(dtype >= ISB_U8 && dtype <= ISB_F64, "bad dtype");
+    ISB_REQUIRE(lm_bank_ok(NP, orient, n_batt),
+                "filter bank layout must be the full (8 orientations, 80 padded filters, 20 batteries) or the short one (4, 48, 15)");
+    ISB_REQUIRE(bg_radius >= 0 && (bg_radius == 0 || bg_weights), "background weights missing");
+    LmWs w;
+    size_t need = carve_lm(w, ws, ws_bytes, H, W, nb, n_batt);
+    ISB_REQUIRE(need <= ws_bytes, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ISB_PROF_LM, st);
+    ISB_CUDA_CHECK(cudaMemsetAsync(w.acc, 0, sizeof(double) * lm_acc_doubles(nb, n_batt), st));
+    ISB_CUDA_CHECK(cudaMemsetAsync(w.counts, 0, sizeof(int) * (size_t)nb, st));
+    if (int rc = lm_accumulate(img, dtype, seg, H, W, 0, H, nb, bg_weights, bg_radius, chmix_host, w_tc, orient, n_batt, w, w.acc, w.counts, st))
+        return rc;
+    const size_t n3 = (size_t)nb * n_batt * 3;
+    k_lm_finalize<<<(nb * n_batt + 255) / 256, 256, 0, st>>>(nb, n_batt, flags, w.acc, w.acc + n3, w.acc + 2 * n3, w.counts, feat, ld, col0);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
+// Row-band mode (one image over several GPUs): the slab img [slab_rows][W][3] holds the rows this band owns, [y_first, y_end) in slab
+// coordinates, plus a halo of the background radius + 16 rows on every side that is not an image border (at an image border the slab
+// ends and the reflection there is the image's own).  The sums of the owned rows are ADDED to acc (isb_lm_acc_doubles doubles, zeroed
+// by the caller) and counts [nb]; after the bands' accumulators are summed, isb_lm_texture_finish forms the features.
+extern "C" int isb_lm_texture_accumulate(const void* img, int dtype, const int32_t* seg, int slab_rows, int W, int y_first, int y_end, int nb,
+                                         const double* bg_weights, int bg_radius, const double* chmix_host, const float* w_tc, int NP,
+                                         int orient, int n_batt, double* acc, int32_t* counts, void* ws, size_t ws_bytes, isb_stream_t stream)
+{
+    ISB_REQUIRE(img && seg && w_tc && acc && counts && ws && chmix_host, "null pointer");
+    ISB_REQUIRE(slab_rows > 0 && W > 0 && nb > 0 && y_first >= 0 && y_first < y_end && y_end <= slab_rows, "bad sizes");
+    ISB_REQUIRE(dtype >= ISB_U8 && dtype <= ISB_F64, "bad dtype");
+    ISB_REQUIRE(lm_bank_ok(NP, orient, n_batt),
+                "filter bank layout must be the full (8 orientations, 80 padded filters, 20 batteries) or the short one (4, 48, 15)");
+    ISB_REQUIRE(bg_radius >= 0 && (bg_radius == 0 || bg_weights), "background weights missing");
+    LmWs w;
+    size_t need = carve_lm(w, ws, ws_bytes, slab_rows, W, nb, n_batt);
+    ISB_REQUIRE(need <= ws_bytes, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ISB_PROF_LM, st);
+    return lm_accumulate(img, dtype, seg, slab_rows, W, y_first, y_end, nb, bg_weights, bg_radius, chmix_host, w_tc, orient, n_batt, w, acc, counts, st);
+}
+
+extern "C" int isb_lm_texture_finish(int nb, int n_batt, int flags, const double* acc, const int32_t* counts, double* feat, int ld, int col0,
+                                     isb_stream_t stream)
+{
+    ISB_REQUIRE(acc && counts && feat, "null pointer");
+    ISB_REQUIRE(nb > 0 && (n_batt == 20 || n_batt == 15), "bad sizes");
+    const size_t n3 = (size_t)nb * n_batt * 3;
+    k_lm_finalize<<<(nb * n_batt + 255) / 256, 256, 0, (cudaStream_t)stream>>>(nb, n_batt, flags, acc, acc + n3, acc + 2 * n3, counts, feat, ld, col0);
     ISB_LAUNCH_CHECK();
     return ISB_OK;
 }

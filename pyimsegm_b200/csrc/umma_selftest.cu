@@ -29,12 +29,32 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const float* __restrict__
     }
     if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
     fence_proxy_async();
-    if (warp == 0) tmem_alloc(smem_u32(&tmem_base), 128);
+    const uint32_t ncols = variant == 2 ? 512u : 128u;
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base), ncols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = tmem_base;
-    if (tid == 0) {
+    constexpr uint32_t A_COL = 256;     // variant 2: A in tensor memory, lane = row, column A_COL + k
+    if (variant == 2) {
+        for (int kk = 0; kk < K / 8; ++kk) {
+            uint32_t r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(A[(size_t)tid * K + kk * 8 + j]);
+            tmem_st8(tbase + ((uint32_t)(warp * 32) << 16) + A_COL + kk * 8, r);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    if (tid == 0 && variant == 2) {
+        const uint32_t idesc = instr_desc(FMT_TF32, 128, N);
+        const uint32_t b_lbo = (uint32_t)(N >> 3) * 128;
+        for (int kk = 0; kk < K / 8; ++kk)
+            mma_tf32_ts(tbase, tbase + A_COL + kk * 8, smem_desc(smem_u32(sB) + kk * 2 * b_lbo, b_lbo, 128), idesc, kk > 0);
+        tc_commit(smem_u32(&bar));
+    } else if (tid == 0) {
         const uint32_t idesc = instr_desc(FMT_TF32, 128, N);
         const uint32_t a_lbo = 16 * 128, b_lbo = (uint32_t)(N >> 3) * 128, sbo = 128;
         for (int kk = 0; kk < K / 8; ++kk) {
@@ -56,15 +76,71 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const float* __restrict__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, 128);
+    if (warp == 0) tmem_dealloc(tbase, ncols);
+}
+
+// issue rate of tcgen05.mma kind::tf32 (M = 128, K = 8) for a given N: `reps` instructions back to back by one thread, then one commit.
+// mode bit 0: rotate over the accumulators that fit (instead of one), bit 1: A from tensor memory (instead of shared memory)
+__global__ void __launch_bounds__(128) k_umma_rate(int N, int reps, int mode, long long* cycles)
+{
+    extern __shared__ __align__(128) unsigned char sm[];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (128 + 256) * 8; i += 128) ((float*)sm)[i] = 0.f;
+    if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
+    fence_proxy_async();
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_base;
+    {   // zero the A columns (496..503) so that no NaN pattern is multiplied
+        uint32_t z[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        tmem_st8(tbase + ((uint32_t)(warp * 32) << 16) + 496, z);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    if (tid == 0) {
+        const uint32_t idesc = instr_desc(FMT_TF32, 128, N);
+        const int nacc = (mode & 1) ? max(1, 496 / N) : 1;
+        const uint64_t ad = smem_desc(smem_u32(sm), 16 * 128, 128);
+        const uint64_t bd = smem_desc(smem_u32(sm) + 128 * 8 * 4, (uint32_t)(N >> 3) * 128, 128);
+        const long long t0 = clock64();
+        int acc = 0;
+        for (int i = 0; i < reps; ++i) {
+            const uint32_t d = tbase + acc * N;
+            if (mode & 2) mma_tf32_ts(d, tbase + 496, bd, idesc, 1u); else mma_tf32(d, ad, bd, idesc, 1u);
+            if (++acc == nacc) acc = 0;
+        }
+        tc_commit(smem_u32(&bar));
+        mbar_wait(smem_u32(&bar), 0);
+        cycles[blockIdx.x] = clock64() - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
 } // namespace
+
+// dev / profiling aid: cycles[b] = clocks CTA b needed for `reps` instructions (see k_umma_rate); `ctas` CTAs run the same loop side by side
+extern "C" int isb_umma_rate(int N, int reps, int mode, int ctas, long long* cycles, isb_stream_t stream)
+{
+    ISB_REQUIRE(cycles && N >= 16 && N <= 256 && N % 16 == 0 && reps > 0 && ctas > 0, "bad arguments");
+    const size_t smem = (128 + 256) * 8 * 4;
+    k_umma_rate<<<ctas, 128, smem, (cudaStream_t)stream>>>(N, reps, mode, cycles);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
 
 extern "C" int isb_umma_selftest(const float* A, const float* B, int N, int K, int variant, float* D, isb_stream_t stream)
 {
     ISB_REQUIRE(A && B && D, "null pointer");
     ISB_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 8 && K <= 64 && K % 8 == 0, "N must be a multiple of 16 <= 256, K a multiple of 8 <= 64");
+    ISB_REQUIRE(variant >= 0 && variant <= 2, "variant: 0 / 1 = A from shared memory (descriptor field order), 2 = A from tensor memory");
     const size_t smem = sizeof(float) * (size_t)(128 + N) * K;
     ISB_CUDA_CHECK(cudaFuncSetAttribute(k_umma_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_umma_selftest<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, N, K, variant, D);

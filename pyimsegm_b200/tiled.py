@@ -33,20 +33,22 @@ OP_SUM_I64, OP_MAX_I64, OP_MIN_F64, OP_MAX_F64, OP_SUM_F64 = 0, 1, 2, 3, 4
 
 class Band(object):
     """rows of one band: owned [own_lo, own_hi), k-means slab [km_lo, km_hi) = owned +- halo, raw slab = k-means slab +-
-    blur radius (all clipped to the image)"""
+    blur radius, uploaded rows [up_lo, up_hi) = the raw slab or owned +- ``margin`` (what a descriptor with a wide footprint
+    asks for), whichever reaches further (all clipped to the image)"""
 
-    def __init__(self, index, own_lo, own_hi, H, halo, radius):
+    def __init__(self, index, own_lo, own_hi, H, halo, radius, margin=0):
         self.index = index
         self.own_lo, self.own_hi = own_lo, own_hi
         self.km_lo, self.km_hi = max(own_lo - halo, 0), min(own_hi + halo, H)
         self.raw_lo, self.raw_hi = max(self.km_lo - radius, 0), min(self.km_hi + radius, H)
+        self.up_lo, self.up_hi = min(self.raw_lo, max(own_lo - margin, 0)), max(self.raw_hi, min(own_hi + margin, H))
 
     def __repr__(self):
         return 'Band(%d: own %d:%d, slab %d:%d, raw %d:%d)' % (self.index, self.own_lo, self.own_hi, self.km_lo, self.km_hi,
                                                             self.raw_lo, self.raw_hi)
 
 
-def plan_bands(H, n_bands, halo, radius):
+def plan_bands(H, n_bands, halo, radius, margin=0):
     """equal bands of ceil(H / n_bands) rows (the last one takes what is left); every band must own at least one row"""
     rows = -(-int(H) // int(n_bands))
     bands = []
@@ -54,7 +56,7 @@ def plan_bands(H, n_bands, halo, radius):
         lo, hi = b * rows, min((b + 1) * rows, H)
         if lo >= hi:
             raise ValueError('an image of %d rows cannot be cut into %d bands of %d rows' % (H, n_bands, rows))
-        bands.append(Band(b, lo, hi, H, halo, radius))
+        bands.append(Band(b, lo, hi, H, halo, radius, margin))
     return bands
 
 
@@ -105,15 +107,17 @@ def _combine(lib, dst_ptr, src_ptr, n, op):
 
 def slic_tiled(image, n_segments, compactness, sigma=1.0, max_iter=10, slic_zero=False, rescale=True, comm=None,
                bands_per_rank=1, eng=None, min_size_factor=0.5, max_size_factor=3, enforce_connectivity=True, defer_check=False,
-               force_whole=False):
+               force_whole=False, raw_margin=0):
     """ SLIC of one host image over the bands of ``comm`` (every rank passes the same image; it uploads only its rows)
 
     :param ndarray image: [H, W, C] host array, C in {1, 3}, dtype uint8 / uint16 / float32 / float64
     :return TiledSuperpixels: ``d_seg`` = the whole label map on this GPU (identical on every rank), ``d_raw[i]`` = the raw
-        image rows ``bands[local[i]].raw_lo:raw_hi`` still on the device for the descriptors
+        image rows ``bands[local[i]].up_lo:up_hi`` still on the device for the descriptors
     :param bool defer_check: do not synchronise to read the orphan counter ``res.d_err``; the caller reads it with its own
         results and calls again with ``force_whole=True`` when it is not zero
     :param bool force_whole: skip the banded sweeps, every rank runs them on the whole image (the fallback)
+    :param int raw_margin: keep at least this many raw rows above and below the owned ones on the device (``d_raw[i]`` then holds
+        the rows ``bands[local[i]].up_lo:up_hi``) -- the Leung-Malik descriptor needs its background radius + 16
     """
     eng = eng or get_engine()
     torch, lib = eng.torch, eng.lib
@@ -134,7 +138,7 @@ def slic_tiled(image, n_segments, compactness, sigma=1.0, max_iter=10, slic_zero
     step = float(max(1, ty, tx))
     halo = 2 * ty + 1
     n_bands = comm.world * int(bands_per_rank)
-    bands = plan_bands(H, n_bands, halo, radius)
+    bands = plan_bands(H, n_bands, halo, radius, int(raw_margin))
     local = list(range(comm.rank * bands_per_rank, (comm.rank + 1) * bands_per_rank))
     owner = lambda b: b // bands_per_rank  # noqa: E731
 
@@ -149,10 +153,10 @@ def slic_tiled(image, n_segments, compactness, sigma=1.0, max_iter=10, slic_zero
     res.d_raw = []
     for i, b in enumerate(local):
         bd = bands[b]
-        raw = eng.to_device(image[bd.raw_lo:bd.raw_hi], 'tb%d_raw' % i)
+        raw = eng.to_device(image[bd.up_lo:bd.up_hi], 'tb%d_raw' % i)
         res.d_raw.append(raw)
         if rescale:
-            own_ptr = raw.data_ptr() + (bd.own_lo - bd.raw_lo) * W * Cn * itemsize
+            own_ptr = raw.data_ptr() + (bd.own_lo - bd.up_lo) * W * Cn * itemsize
             tgt = mm if i == 0 else mm_b
             _lib.check(lib.isb_image_minmax(C.c_void_p(own_ptr), code, C.c_longlong((bd.own_hi - bd.own_lo) * W * Cn), _lib.ptr(tgt), st))
             if i > 0:
@@ -172,7 +176,8 @@ def slic_tiled(image, n_segments, compactness, sigma=1.0, max_iter=10, slic_zero
         bd = bands[b]
         hraw = bd.raw_hi - bd.raw_lo
         lab = eng.buf('tb%d_lab' % i, (3, hraw, W), torch.float64)
-        _lib.check(lib.isb_slic_prepare(_lib.ptr(res.d_raw[i]), code, hraw, W, Cn, w_half.ctypes.data_as(C.POINTER(C.c_double)), radius,
+        raw_ptr = C.c_void_p(res.d_raw[i].data_ptr() + (bd.raw_lo - bd.up_lo) * W * Cn * itemsize)
+        _lib.check(lib.isb_slic_prepare(raw_ptr, code, hraw, W, Cn, w_half.ctypes.data_as(C.POINTER(C.c_double)), radius,
                                         C.c_double(1.0 / compactness), 2 if rescale else 0, _lib.ptr(lab), _lib.ptr(mm), st))
         slab_rows = bd.km_hi - bd.km_lo
         labels = eng.buf('tb%d_labels' % i, (slab_rows, W), torch.int32)
@@ -238,7 +243,7 @@ def slic_tiled(image, n_segments, compactness, sigma=1.0, max_iter=10, slic_zero
     return res
 
 
-def color_stats_tiled(res, image_dtype, channels, flags, comm=None, eng=None):
+def color_stats_tiled(res, image_dtype, channels, flags, comm=None, eng=None, feat=None, col0=0):
     """colour statistics + centroids of the banded image over ``res.d_seg``: every band accumulates its owned rows, the
     accumulators are summed over the GPUs, every GPU finishes the same [nb, 3*len(flags)] table"""
     eng = eng or get_engine()
@@ -261,7 +266,7 @@ def color_stats_tiled(res, image_dtype, channels, flags, comm=None, eng=None):
 
     def rows(i, b):
         bd = res.bands[b]
-        img_ptr = res.d_raw[i].data_ptr() + (bd.own_lo - bd.raw_lo) * W * 3 * itemsize
+        img_ptr = res.d_raw[i].data_ptr() + (bd.own_lo - bd.up_lo) * W * 3 * itemsize
         seg_ptr = res.d_seg.data_ptr() + bd.own_lo * W * 4
         return bd, C.c_void_p(img_ptr), C.c_void_p(seg_ptr)
 
@@ -282,10 +287,79 @@ def color_stats_tiled(res, image_dtype, channels, flags, comm=None, eng=None):
                                                        _lib.ptr(meanf), _lib.ptr(var), st))
         comm.all_reduce(var, 'sum')
     ncol = 3 * bin(bits).count('1')
-    feat = eng.buf('feat', (nb, max(ncol, 1)), torch.float64)
+    if feat is None:
+        feat = eng.buf('feat', (nb, max(ncol, 1)), torch.float64)
     centres = eng.buf('centres', (nb, 2), torch.float64)
-    _lib.check(lib.isb_segment_stats_finish(nb, bits, _lib.ptr(acc), _lib.ptr(var), _lib.ptr(iacc), _lib.ptr(feat), int(feat.shape[1]), 0,
-                                            _lib.ptr(centres), None, st))
+    _lib.check(lib.isb_segment_stats_finish(nb, bits, _lib.ptr(acc), _lib.ptr(var), _lib.ptr(iacc), _lib.ptr(feat), int(feat.shape[1]),
+                                            int(col0), _lib.ptr(centres), None, st))
+    res.d_feat, res.d_centres = feat, centres
+    return feat, centres
+
+
+LM_ROW_MARGIN = 616     # rows of the Leung-Malik descriptor's footprint: sigma-150 background (radius 600) + half a 33 x 33 kernel
+
+
+def texture_stats_tiled(res, image_dtype, flags, bank_type='normal', comm=None, eng=None, feat=None, col0=0):
+    """Leung-Malik texture statistics (reference descriptors.py:1041-1106) of the banded image over ``res.d_seg``: every band runs
+    the background subtraction and the filter-bank contraction on its rows + ``LM_ROW_MARGIN`` rows of halo (``slic_tiled`` must
+    have been called with ``raw_margin=LM_ROW_MARGIN``) and accumulates the sums of the rows it owns; the accumulators -- the
+    per-superpixel sums and the per-battery response norms of the WHOLE image -- are summed over the GPUs, every GPU finishes
+    the same [nb, n_batteries * 3 * len(flags)] block of ``feat``"""
+    from .texture import _device_bank, background_kernel
+    eng = eng or get_engine()
+    torch, lib = eng.torch, eng.lib
+    comm = comm or default_comm()
+    H, W = res.shape
+    code = _lib.DTYPE_CODES[str(np.dtype(image_dtype))]
+    itemsize = np.dtype(image_dtype).itemsize
+    nb = int(res.nb_bound)
+    st = _lib.stream_ptr()
+    bits = 0
+    for f in flags:
+        bits |= FLAG_BITS[f]
+    _, d_w, NP, orient, n_batt = _device_bank(bank_type)
+    w_bg, radius, mix = background_kernel()
+    d_wbg = eng.const_device(w_bg, 'lm_bg_w')
+    acc = eng.buf('tb_lm_acc', (int(lib.isb_lm_acc_doubles(nb, n_batt)),), torch.float64)
+    counts = eng.buf('tb_lm_counts', (nb,), torch.int32)
+    acc.zero_()
+    counts.zero_()
+    for i, b in enumerate(res.local):
+        bd = res.bands[b]
+        lo, hi = max(bd.own_lo - LM_ROW_MARGIN, 0), min(bd.own_hi + LM_ROW_MARGIN, H)
+        if lo < bd.up_lo or hi > bd.up_hi:
+            raise ValueError('the band keeps the raw rows %d:%d, the texture descriptor needs %d:%d (slic_tiled raw_margin)'
+                             % (bd.up_lo, bd.up_hi, lo, hi))
+        img_ptr = C.c_void_p(res.d_raw[i].data_ptr() + (lo - bd.up_lo) * W * 3 * itemsize)
+        seg_ptr = C.c_void_p(res.d_seg.data_ptr() + lo * W * 4)
+        wsb = lib.isb_lm_workspace_bytes(hi - lo, W, nb, n_batt)
+        ws = eng.buf('ws_lm', (wsb,), torch.uint8)
+        _lib.check(lib.isb_lm_texture_accumulate(img_ptr, code, seg_ptr, hi - lo, W, bd.own_lo - lo, bd.own_hi - lo, nb, _lib.ptr(d_wbg), radius,
+                                                 mix.ctypes.data_as(C.POINTER(C.c_double)), _lib.ptr(d_w), NP, orient, n_batt,
+                                                 _lib.ptr(acc), _lib.ptr(counts), _lib.ptr(ws), C.c_size_t(wsb), st))
+    comm.all_reduce(acc, 'sum')
+    comm.all_reduce(counts, 'sum')
+    ncol = n_batt * 3 * bin(bits).count('1')
+    if feat is None:
+        feat = eng.buf('feat_lm', (nb, ncol), torch.float64)
+    _lib.check(lib.isb_lm_texture_finish(nb, n_batt, bits, _lib.ptr(acc), _lib.ptr(counts), _lib.ptr(feat), int(feat.shape[1]), int(col0), st))
+    return feat
+
+
+def features_tiled(res, image_dtype, channels, layout, ncol, comm=None, eng=None):
+    """the [nb, ncol] feature table of ``native_feature_layout`` over the banded image (``res.d_feat``) + the centroids"""
+    eng = eng or get_engine()
+    feat = eng.buf('feat', (int(res.nb_bound), max(ncol, 1)), eng.torch.float64)
+    centres = None
+    for key, flags, col0, _ in layout:
+        if key == 'color':
+            _, centres = color_stats_tiled(res, image_dtype, channels, flags, comm=comm, eng=eng, feat=feat, col0=col0)
+        else:
+            texture_stats_tiled(res, image_dtype, flags, 'short' if key.endswith('_short') else 'normal', comm=comm, eng=eng, feat=feat,
+                                col0=col0)
+    if centres is None:
+        _, centres = color_stats_tiled(res, image_dtype, channels, (), comm=comm, eng=eng, feat=eng.buf('feat_none', (int(res.nb_bound), 1),
+                                                                                                         eng.torch.float64))
     res.d_feat, res.d_centres = feat, centres
     return feat, centres
 
@@ -300,17 +374,18 @@ def pipe_color2d_slic_features_model_graphcut_tiled(image, nb_classes, dict_feat
         ``segm`` is the whole [H, W] map on every rank (``segm_soft`` stays banded: it is 8*K bytes per pixel)
     """
     from . import graph_cuts
-    from .descriptors import native_feature_layout
+    from .descriptors import flags_are_native, native_feature_layout
     from .graph_cuts import compute_pairwise_cost
     from .pipelines import EDGE_CAP_PER_NODE, _edge_mode
     from .superpixels import _as_rgb_like, _supported_dtype, slic_params
     if sp_regul <= 0.:
         raise ValueError('slic. regularisation must be positive')
     dict_features = {'color': ['mean']} if dict_features is None else dict_features
-    layout, _ = native_feature_layout(dict_features)
-    if [k for k, _, _, _ in layout] != ['color']:
-        raise NotImplementedError('the banded path computes the colour statistics only (got %r)' % sorted(dict_features))
-    flags = layout[0][1]
+    layout, ncol = native_feature_layout(dict_features)
+    if not layout or not flags_are_native(dict_features):
+        raise NotImplementedError('the banded path computes mean / std / energy of the colours and of the Leung-Malik responses (got %r)'
+                                  % dict_features)
+    margin = LM_ROW_MARGIN if any(k.startswith('tLM') for k, _, _, _ in layout) else 0
     eng = get_engine()
     torch, lib = eng.torch, eng.lib
     comm = comm or default_comm()
@@ -326,8 +401,8 @@ def pipe_color2d_slic_features_model_graphcut_tiled(image, nb_classes, dict_feat
     while True:
         if redo_front:
             res = slic_tiled(image, n_seg, compact, sigma=1.0, comm=comm, bands_per_rank=bands_per_rank, eng=eng, defer_check=True,
-                             force_whole=force_whole)
-            color_stats_tiled(res, image.dtype, int(image.shape[2]), flags, comm=comm, eng=eng)
+                             force_whole=force_whole, raw_margin=margin)
+            features_tiled(res, image.dtype, int(image.shape[2]), layout, ncol, comm=comm, eng=eng)
             nb = int(res.nb_bound)
             d_proba, _ = eng.gmm_fit_predict(res.d_feat, K, n_init, max_iter, use_scaler, graph_cuts.RANDOM_SEED, d_n=res.d_n_labels)
             redo_front = False

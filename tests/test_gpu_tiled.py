@@ -109,6 +109,39 @@ def test_banded_colour_statistics_match_oracle(oracle, eng):
     np.testing.assert_allclose(eng.to_host(centres)[:nb], np.asarray(oracle.superpixel_centers(seg)), rtol=1e-12)
 
 
+@pytest.mark.parametrize('bank', ['normal', 'short'])
+def test_banded_texture_statistics_match_whole_image(eng, bank):
+    """Leung-Malik statistics of a banded image: bands whose slabs end INSIDE the image (rows + 616 of halo) must reproduce the
+    whole-image descriptor -- same background, same responses on the owned rows, same image-wide response norms"""
+    from pyimsegm_b200.superpixels import slic_params
+    from pyimsegm_b200.texture import device_lm_features
+    from pyimsegm_b200.tiled import LM_ROW_MARGIN, slic_tiled, texture_stats_tiled
+    rng = np.random.RandomState(5)
+    img = synth_regions(2000, 192, seed=21)[0] + 0.05 * rng.standard_normal((2000, 192, 3))
+    n_seg, compact = slic_params(img.shape[:2], 24, 0.2)
+    flags = ('mean', 'std', 'energy')
+    res = slic_tiled(img, n_seg, compact, bands_per_rank=3, eng=eng, raw_margin=LM_ROW_MARGIN)
+    assert res.bands[1].up_lo > 0 and res.bands[1].up_hi < 2000          # the middle band's slab has two interior edges
+    got = eng.to_host(texture_stats_tiled(res, img.dtype, flags, bank, eng=eng)).copy()
+    d_img = eng.to_device(img, 'image')
+    want = eng.to_host(device_lm_features(eng, d_img, res.d_seg, int(res.nb_bound), flags, bank)[0]).copy()
+    assert np.abs(want).max() > 0.1
+    np.testing.assert_allclose(got, want, rtol=1e-7, atol=1e-9)
+
+
+def test_banded_pipeline_with_texture_matches_single_gpu_pipeline(eng):
+    from pyimsegm_b200 import pipelines as pl
+    from pyimsegm_b200.tiled import pipe_color2d_slic_features_model_graphcut_tiled
+    rng = np.random.RandomState(6)
+    img = synth_regions(1500, 160, seed=22)[0] + 0.05 * rng.standard_normal((1500, 160, 3))
+    fts = {'color': ['mean', 'std'], 'tLM_short': ['mean', 'energy']}
+    segm, soft = pl.pipe_color2d_slic_features_model_graphcut(img, 3, fts, sp_size=20, sp_regul=0.2, gc_regul=1., gc_edge_type='model')
+    got, got_soft, (lo, hi) = pipe_color2d_slic_features_model_graphcut_tiled(img, 3, fts, sp_size=20, sp_regul=0.2, bands_per_rank=2)
+    assert (lo, hi) == (0, 1500)
+    assert np.mean(got == segm) > 0.999
+    np.testing.assert_allclose(got_soft, soft, rtol=1e-4, atol=1e-6)
+
+
 def test_two_ranks_nccl():
     """the same checks with two processes, one GPU each, merged by NCCL all_reduce / broadcast"""
     import torch

@@ -38,3 +38,17 @@ def test_tcgen05_tf32_gemm_known_answer(N, K):
     if err > 1e-4:
         alt = np.abs(_run(lib, torch, A, B, 1) - want).max()
         raise AssertionError('tcgen05 GEMM wrong: max err %g (with LBO/SBO swapped: %g)' % (err, alt))
+
+
+@pytest.mark.parametrize('N,K', [(80, 40), (48, 40), (240, 64)])
+def test_tcgen05_tf32_gemm_a_operand_in_tensor_memory(N, K):
+    """the TS form: A written into tensor memory with tcgen05.st (lane = row, one column per tf32 element), B from shared memory"""
+    from pyimsegm_b200 import _lib
+    torch = _lib.require_cuda()
+    lib = _lib.lib()
+    rng = np.random.RandomState(7 * N + K)
+    A = _tf32(rng.standard_normal((128, K)).astype(np.float32))
+    B = _tf32(rng.standard_normal((N, K)).astype(np.float32))
+    want = A.astype(np.float64) @ B.astype(np.float64).T
+    got = _run(lib, torch, A, B, 2)
+    assert np.abs(got - want).max() <= 1e-4
