@@ -10,10 +10,9 @@
 //     (a thread owns a column and 16 consecutive output rows, the 1201 weights slide through registers), the other axis
 //     reuses it on a transposed copy; the channel axis (length 3, reflected 1201-tap kernel) folds into a 3x3 mix.
 // (2) contraction: implicit GEMM  response[pixel, filter] = sum_taps patch[pixel, tap] * K[tap, filter]  on the TENSOR
-//     cores: mma.sync.m16n8k8 TF32 with the 3xTF32 split (a_hi b_hi + a_hi b_lo + a_lo b_hi, FP32 accumulate), which
-//     keeps the result at f32 accuracy -- the reference rounds every response to f32 before its statistics
-//     (descriptors.py:233).  A fragments are read straight from the shared-memory image tile (shifted windows, no im2col
-//     copy); the pre-split weights stream through a cp.async double buffer, one filter row (33 -> 40 taps) per stage.
+//     cores: tcgen05.mma kind::tf32 with the 3xTF32 split (a_hi b_hi + a_hi b_lo + a_lo b_hi, FP32 accumulate in tensor memory),
+//     which keeps the result at f32 accuracy -- the reference rounds every response to f32 before its statistics
+//     (descriptors.py:233).  Source rows and the pre-split weights arrive by TMA; the patch matrices live in tensor memory.
 //     FLOPs: 3 channels x 76 kernels x 33^2 x 2 = 496 584 per pixel (x3 for the split).
 // (3) epilogue, fused: max over the orientations of a battery (quad shuffles), clip, then sum r and sum r^2 per
 //     (superpixel, battery, channel) and globally per battery -- the responses are never written to memory.  The
@@ -21,14 +20,12 @@
 // Tolerance against the float64 oracle: 2e-4 relative on the features (stated in tests/test_gpu_texture.py).
 #include "common.cuh"
 #include "umma.cuh"
-#include <stdlib.h>
-#include <string.h>
 
 namespace {
 
 // ---------------------------------------------------------------- (1) background ----------------------------------------------------
 
-constexpr int VB_R = 16;      // output rows per thread
+constexpr int VB_R = 32;      // output rows per thread
 constexpr int VB_T = 128;     // threads (columns) per CTA
 
 __device__ __forceinline__ int reflect_idx(int i, int n)
@@ -49,46 +46,74 @@ __global__ void __launch_bounds__(256) k_lm_to_planar(const void* __restrict__ i
 }
 
 // blur along axis 0 of [planes][n0][n1] (n1 contiguous).  wfull: 2*radius+1 weights (symmetric), in global memory.
+// A thread owns one column and R consecutive output rows.  Input rows are taken R at a time: the 2R - 1 weights such a block needs
+// (output row r takes input row t with w[d + t - r]) sit in REGISTERS and slide by R per block -- R weight loads for R^2 FP64 FMAs.
+// Every block of R output rows reads its own 2 radius + R input rows, so the L2 -> SM traffic is (2 radius / R + 1) x the image:
+// R = 32 instead of 16 halves what turned out to be the bound of this kernel (3.2 TB/s of L2 reads at R = 16).
+template <int R, bool FAST_REFLECT>
 __global__ void __launch_bounds__(VB_T) k_lm_vblur(const double* __restrict__ in, int n0, int n1, const double* __restrict__ wfull, int radius,
                                                    double* __restrict__ out)
 {
-    extern __shared__ double s_w[]; // padded weights: index d + radius + VB_R for d in [-(radius+VB_R), radius+VB_R]
-    const int wn = 2 * (radius + VB_R) + 1;
+    // padded weights: s_w[d + radius + 3R] = w[d] for |d| <= radius, 0 for the 3R entries on either side (the last refill of the
+    // register window reads up to 3R - 2 past the radius)
+    extern __shared__ double s_w[];
+    const int pad = radius + 3 * R, wn = 2 * pad + 1;
     for (int i = threadIdx.x; i < wn; i += VB_T) {
-        int d = i - (radius + VB_R);
+        int d = i - pad;
         s_w[i] = (d >= -radius && d <= radius) ? wfull[d + radius] : 0.0;
     }
     __syncthreads();
-    // a thread owns TWO columns (x, x + VB_T) and VB_R consecutive output rows: every weight read from shared memory (a broadcast
-    // to the whole warp) feeds two FP64 FMAs, which balances the shared-memory pipe against the FP64 pipe
-    const int x = blockIdx.x * (2 * VB_T) + threadIdx.x, x2 = x + VB_T;
-    const int y0 = blockIdx.y * VB_R;
+    const int x = blockIdx.x * VB_T + threadIdx.x;
+    const int y0 = blockIdx.y * R;
     const size_t plane = (size_t)blockIdx.z * n0 * n1;
     if (x >= n1) return;
-    const bool two = x2 < n1;
-    double acc[2][VB_R];
+    double acc[R];
 #pragma unroll
-    for (int r = 0; r < VB_R; ++r) { acc[0][r] = 0.0; acc[1][r] = 0.0; }
-    // input rows i = y0 - radius .. y0 + VB_R - 1 + radius; output row y0 + r uses weight w[i - (y0 + r)]
-    const int i_beg = y0 - radius, i_end = y0 + VB_R - 1 + radius;
-    const double* wc = s_w + (radius + VB_R); // wc[d]
-    for (int i = i_beg; i <= i_end; ++i) {
-        const size_t row = plane + (size_t)reflect_idx(i, n0) * n1;
-        const double v0 = in[row + x], v1 = two ? in[row + x2] : 0.0;
-        const int d0 = i - y0;
+    for (int r = 0; r < R; ++r) acc[r] = 0.0;
+    // input rows i = y0 - radius .. y0 + R - 1 + radius (rounded up to whole blocks: the extra rows meet zero weights);
+    // output row y0 + r uses weight w[i - (y0 + r)]
+    const int n_blocks = (2 * radius + R + R - 1) / R;
+    const double* wc = s_w + pad; // wc[d]
+    double w[2 * R - 1];          // w[j] = wc[db - (R - 1) + j], db = offset of the block's first input row from output row y0
+    int db = -radius;
 #pragma unroll
-        for (int r = 0; r < VB_R; ++r) {
-            const double wgt = wc[d0 - r];
-            acc[0][r] = fma(wgt, v0, acc[0][r]);
-            acc[1][r] = fma(wgt, v1, acc[1][r]);
+    for (int j = 0; j < 2 * R - 1; ++j) w[j] = wc[db - (R - 1) + j];
+    const double* col = in + plane + x;
+    for (int blk = 0; blk < n_blocks; ++blk, db += R) {
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+            int i = y0 + db + t;
+            // one reflection is enough when radius + 2R <= n0 (FAST_REFLECT); the general form handles images smaller than the kernel
+            if (FAST_REFLECT) i = i < 0 ? -1 - i : (i >= n0 ? 2 * n0 - 1 - i : i);
+            else i = reflect_idx(i, n0);
+            const double v = col[(size_t)i * n1];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = fma(w[R - 1 + t - r], v, acc[r]);
         }
+#pragma unroll
+        for (int j = 0; j < R - 1; ++j) w[j] = w[j + R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) w[R - 1 + j] = wc[db + R + j];
     }
 #pragma unroll
-    for (int r = 0; r < VB_R; ++r)
-        if (y0 + r < n0) {
-            out[plane + (size_t)(y0 + r) * n1 + x] = acc[0][r];
-            if (two) out[plane + (size_t)(y0 + r) * n1 + x2] = acc[1][r];
-        }
+    for (int r = 0; r < R; ++r)
+        if (y0 + r < n0) out[plane + (size_t)(y0 + r) * n1 + x] = acc[r];
+}
+
+static int launch_vblur(const double* in, int n0, int n1, const double* w, int radius, double* out, cudaStream_t st)
+{
+    const size_t smem = sizeof(double) * (2 * (size_t)(radius + 3 * VB_R) + 1);
+    ISB_REQUIRE(smem <= 200 * 1024, "background radius too large");
+    const dim3 grid((n1 + VB_T - 1) / VB_T, (n0 + VB_R - 1) / VB_R, 3);
+    if (radius + 2 * VB_R <= n0) {
+        ISB_CUDA_CHECK(cudaFuncSetAttribute(k_lm_vblur<VB_R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_lm_vblur<VB_R, true><<<grid, VB_T, smem, st>>>(in, n0, n1, w, radius, out);
+    } else {
+        ISB_CUDA_CHECK(cudaFuncSetAttribute(k_lm_vblur<VB_R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_lm_vblur<VB_R, false><<<grid, VB_T, smem, st>>>(in, n0, n1, w, radius, out);
+    }
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
 }
 
 // [planes][n0][n1] -> [planes][n1][n0]
@@ -131,22 +156,21 @@ __global__ void __launch_bounds__(256) k_lm_mix_sub(const double* __restrict__ i
 
 // ---------------------------------------------------------------- (2)+(3) contraction + statistics ---------------------------------
 //
-// Implicit GEMM on the 5th-generation tensor cores: tcgen05.mma kind::tf32, accumulators in tensor memory.
+// Implicit GEMM on the 5th-generation tensor cores: tcgen05.mma kind::tf32, accumulators AND the A operand in tensor memory.
 //   M = 128 consecutive pixels of one image row, N = the padded filter count (80 full bank / 48 short bank),
 //   K = the 33 taps of one kernel row padded to 40 (5 instructions of K = 8), one such product per (output row, kernel row).
 // A CTA (persistent, one per SM) owns tiles of TR = 3 output rows x 128 pixels of one channel.  For every SOURCE row s of the
-// tile (3 + 32 of them) the patch matrix A_s[m][k] = row_s[x0 + m + k] is written ONCE into shared memory in the K-major core-matrix
-// layout and used for every output row r with kernel row dy = s - r:  acc[r] += A_s * B_dy^T.
+// tile (3 + 32 of them) the patch matrix A_s[m][k] = row_s[x0 + m + k] is formed ONCE and used for every output row r with kernel
+// row dy = s - r:  acc[r] += A_s * B_dy^T.
 // 3xTF32: image and weights are pre-split into a tf32 value and a tf32 remainder; acc += a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
 // (FP32 accumulate) keeps f32 accuracy -- the reference rounds every response to f32 before its statistics (descriptors.py:233).
 // Warp roles (448 threads):
-//   warp 0     TMA: the split weights of kernel row dy (one contiguous slice in operand layout, cp.async.bulk) into a 4-slot ring,
-//              and the source rows (2-D tensor-map loads of the reflect-padded hi / lo planes) into a 4-slot ring
+//   warp 0     TMA: the split weights of kernel row dy (cp.async.bulk, one piece per lane) into the weight ring, the source rows
+//              (2-D tensor-map loads of the reflect-padded hi / lo planes) into a 4-slot ring
 //   warp 1     allocates tensor memory; one lane issues every tcgen05.mma and the commits that free the rings
-//   warps 2-9  patch-matrix producers: raw row -> A_s (hi, lo), two stages (two threads per pixel, half of the k chunks each)
+//   warps 2-9  patch-matrix producers: raw row -> A_s (hi, lo) in tensor memory (tcgen05.st), a lane quarter per warp
 //   warps 10-13 epilogue: tcgen05.ld the 3 x N accumulators of a pixel, max over the orientations of a battery, clip, then
 //              run-length sums of r and r^2 along the row per (battery, output row) -> atomics on the per-superpixel sums.
-// Two accumulator buffers (2 x 3 x N <= 480 of the 512 tensor-memory columns): the epilogue of a tile overlaps the MMAs of the next.
 // The responses are never written to memory.
 
 constexpr int KW = 33;                    // kernel edge
@@ -158,11 +182,8 @@ constexpr int TR = 3;                     // output rows per CTA tile
 constexpr int SROWS = TR + KW - 1;        // source rows per tile
 constexpr int RAWW = TM + KPAD;           // floats of one staged source row
 constexpr int RAW_PITCH = 768;            // bytes between the hi and the lo row of a raw slot (TMA destinations 128-byte aligned)
-constexpr int NRAW = 4, NA = 2, NB = 4;   // ring depths: raw rows, patch matrices, weight slices
-constexpr int A_HALF = TM * KPAD * 4;     // bytes of one patch matrix (hi or lo)
-constexpr int A_STAGE = 2 * A_HALF;
-constexpr int A_LBO = (TM / 8) * 128;     // bytes between the two 16-byte K chunks of one MMA (K-major, no swizzle)
-constexpr int LM_PROD = 256;                // patch-matrix producer threads: two per pixel of the M tile, half of the k chunks each
+constexpr int NRAW = 4;                   // ring depth of the staged source rows
+constexpr int LM_PROD = 256;                // patch-matrix producer threads: two per pixel of the M tile (value / remainder)
 constexpr int LM_THREADS = 64 + LM_PROD + 128;
 
 struct LmTcArgs {
@@ -188,236 +209,11 @@ template <int NPAD> __host__ __device__ constexpr int lm_batt_of_col(int col)
     return (col - Bk::GS * Bk::NG) < Bk::NS ? 5 * ((col - Bk::GS * Bk::NG) / 3) + 2 + (col - Bk::GS * Bk::NG) % 3 : -1;
 }
 
-template <int NPAD> struct LmSmem {
-    using Bk = LmBank<NPAD>;
-    static constexpr int B_HALF = NPAD * KPAD * 4;
-    static constexpr int B_SLOT = 2 * B_HALF;
-    static constexpr int B_LBO = (NPAD / 8) * 128;
-    static constexpr int TS = Bk::NBATT + 1;                     // row stride of the battery-value table (floats)
-    static constexpr int OFF_B = 0;
-    static constexpr int OFF_A = OFF_B + NB * B_SLOT;
-    static constexpr int OFF_RAW = OFF_A + NA * A_STAGE;
-    static constexpr int OFF_T = OFF_RAW + NRAW * 2 * RAW_PITCH;
-    static constexpr int OFF_LAB = OFF_T + TR * TM * TS * 4;
-    static constexpr int OFF_BAR = OFF_LAB + TR * TM * 4;
-    static constexpr int N_BAR = 2 * NRAW + 2 * NA + 2 * NB + 4;
-    static constexpr int OFF_TMEM = OFF_BAR + N_BAR * 8;
-    static constexpr int BYTES = OFF_TMEM + 16;
-    static_assert(BYTES <= 227 * 1024, "shared memory budget");
-    static_assert(2 * TR * NPAD <= 512, "tensor memory budget");
-};
-
-template <int NPAD>
-__global__ void __launch_bounds__(LM_THREADS, 1) k_lm_conv_tc(const __grid_constant__ CUtensorMap tmap, LmTcArgs a)
-{
-    using namespace umma;
-    using Sm = LmSmem<NPAD>;
-    using Bk = LmBank<NPAD>;
-    extern __shared__ __align__(1024) unsigned char smem[];
-    const uint32_t sbase = smem_u32(smem);
-    const uint32_t bar0 = sbase + Sm::OFF_BAR;
-    auto raw_full = [&](uint32_t i) { return bar0 + 8u * i; };
-    auto raw_empty = [&](uint32_t i) { return bar0 + 8u * (NRAW + i); };
-    auto a_full = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + i); };
-    auto a_empty = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + NA + i); };
-    auto b_full = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + 2 * NA + i); };
-    auto b_empty = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + 2 * NA + NB + i); };
-    auto acc_full = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + 2 * NA + 2 * NB + i); };
-    auto acc_empty = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + 2 * NA + 2 * NB + 2 + i); };
-    uint32_t* tmem_slot = (uint32_t*)(smem + Sm::OFF_TMEM);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < NRAW; ++i) { mbar_init(raw_full(i), 1); mbar_init(raw_empty(i), LM_PROD); }
-        for (int i = 0; i < NA; ++i) { mbar_init(a_full(i), LM_PROD); mbar_init(a_empty(i), 1); }
-        for (int i = 0; i < NB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), TM); }
-        fence_mbar_init();
-        prefetch_tmap(&tmap);
-    }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tbase = *tmem_slot;
-
-    const int tiles_per_ch = a.tiles_x * a.tiles_y;
-    const int n_tiles = 3 * tiles_per_ch;
-
-    if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer ------------------------------------------------
-        if (lane == 0) {
-            uint32_t jr = 0, jb = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int ch = t / tiles_per_ch, rem = t - ch * tiles_per_ch;
-                const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-                const int x0 = tx * TM, y0 = a.y_first + ty * TR;
-                for (int s = 0; s < SROWS; ++s) {
-                    if (s < KW) {
-                        const uint32_t slot = jb % NB, ph = (jb / NB) & 1;
-                        mbar_wait(b_empty(slot), ph ^ 1);
-                        mbar_arrive_expect_tx(b_full(slot), Sm::B_SLOT);
-                        bulk_g2s(sbase + Sm::OFF_B + slot * Sm::B_SLOT, a.w_tc + (size_t)s * (Sm::B_SLOT / 4), Sm::B_SLOT, b_full(slot));
-                        ++jb;
-                    }
-                    const uint32_t slot = jr % NRAW, ph = (jr / NRAW) & 1;
-                    mbar_wait(raw_empty(slot), ph ^ 1);
-                    mbar_arrive_expect_tx(raw_full(slot), 2 * RAWW * 4);
-                    const uint32_t dst = sbase + Sm::OFF_RAW + slot * 2 * RAW_PITCH;
-                    tma_load_2d(dst, &tmap, x0, ch * a.Hp + y0 + s, raw_full(slot));
-                    tma_load_2d(dst + RAW_PITCH, &tmap, x0, (3 + ch) * a.Hp + y0 + s, raw_full(slot));
-                    ++jr;
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer --------------------------------------------------
-        if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc(FMT_TF32, TM, NPAD);
-            uint32_t jr = 0, jb_base = 0, it = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-                const uint32_t buf = it & 1;
-                mbar_wait(acc_empty(buf), ((it >> 1) & 1) ^ 1);
-                tc_fence_after();
-                for (int s = 0; s < SROWS; ++s) {
-                    const uint32_t st = jr % NA;
-                    if (s < KW) { const uint32_t jb = jb_base + s; mbar_wait(b_full(jb % NB), (jb / NB) & 1); }
-                    mbar_wait(a_full(st), (jr / NA) & 1);
-                    tc_fence_after();
-                    const uint32_t a_hi = sbase + Sm::OFF_A + st * A_STAGE, a_lo = a_hi + A_HALF;
-#pragma unroll
-                    for (int r = 0; r < TR; ++r) {
-                        const int dy = s - r;
-                        if (dy < 0 || dy >= KW) continue;
-                        const uint32_t b_hi = sbase + Sm::OFF_B + ((jb_base + dy) % NB) * Sm::B_SLOT, b_lo = b_hi + Sm::B_HALF;
-                        const uint32_t d = tbase + buf * (TR * NPAD) + r * NPAD;
-#pragma unroll
-                        for (int kk = 0; kk < KPAD / 8; ++kk) {
-                            const uint64_t ah = smem_desc(a_hi + kk * 2 * A_LBO, A_LBO, 128), al = smem_desc(a_lo + kk * 2 * A_LBO, A_LBO, 128);
-                            const uint64_t bh = smem_desc(b_hi + kk * 2 * Sm::B_LBO, Sm::B_LBO, 128);
-                            const uint64_t bl = smem_desc(b_lo + kk * 2 * Sm::B_LBO, Sm::B_LBO, 128);
-                            mma_tf32(d, al, bh, idesc, (dy > 0 || kk > 0) ? 1u : 0u);   // small terms first
-                            mma_tf32(d, ah, bl, idesc, 1u);
-                            mma_tf32(d, ah, bh, idesc, 1u);
-                        }
-                    }
-                    tc_commit(a_empty(st));                                              // the patch matrices of row s are free again
-                    if (s >= TR - 1) tc_commit(b_empty((jb_base + s - (TR - 1)) % NB));  // kernel row s - (TR-1) had its last use
-                    ++jr;
-                }
-                tc_commit(acc_full(buf));
-                jb_base += KW;
-            }
-        }
-    } else if (warp < 2 + LM_PROD / 32) {
-        // ------------------------------------------------------------ patch-matrix producers ---------------------------------------
-        const int m = (threadIdx.x - 64) & (TM - 1), kh = (threadIdx.x - 64) >> 7;   // pixel of the tile, half of the k chunks
-        uint32_t jr = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            for (int s = 0; s < SROWS; ++s, ++jr) {
-                const uint32_t rs = jr % NRAW, st = jr % NA;
-                mbar_wait(raw_full(rs), (jr / NRAW) & 1);
-                mbar_wait(a_empty(st), ((jr / NA) & 1) ^ 1);
-                const float* rh = (const float*)(smem + Sm::OFF_RAW + rs * 2 * RAW_PITCH) + m;
-                const float* rl = rh + RAW_PITCH / 4;
-                float4* dh = (float4*)(smem + Sm::OFF_A + st * A_STAGE) + (m >> 3) * 8 + (m & 7);
-                float4* dl = dh + A_HALF / 16;
-#pragma unroll
-                for (int q = 0; q < KC / 2; ++q) {
-                    const int k4 = kh * (KC / 2) + q;
-                    dh[k4 * (A_LBO / 16)] = make_float4(rh[4 * k4], rh[4 * k4 + 1], rh[4 * k4 + 2], rh[4 * k4 + 3]);
-                    dl[k4 * (A_LBO / 16)] = make_float4(rl[4 * k4], rl[4 * k4 + 1], rl[4 * k4 + 2], rl[4 * k4 + 3]);
-                }
-                fence_proxy_async();          // these st.shared must be visible to the tensor core's (async proxy) operand reads
-                mbar_arrive(a_full(st));
-                mbar_arrive(raw_empty(rs));
-            }
-        }
-    } else {
-        // ------------------------------------------------------------ epilogue ------------------------------------------------------
-        const int e = threadIdx.x - (64 + LM_PROD);   // 0..127
-        const int q = warp & 3;                   // tensor-memory lane quarter this warp may read
-        const int m = 32 * q + lane;
-        float* T = (float*)(smem + Sm::OFF_T);
-        int* s_lab = (int*)(smem + Sm::OFF_LAB);
-        const bool walker = e < 2 * TR * Bk::NBATT;
-        const int p = e >> 1, half = e & 1;
-        const int wr = p / Bk::NBATT, wb = p - wr * Bk::NBATT;
-        double g2 = 0.0;
-        uint32_t it = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-            const int ch = t / tiles_per_ch, rem = t - ch * tiles_per_ch;
-            const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-            const int x0 = tx * TM, y0 = a.y_first + ty * TR;
-            const uint32_t buf = it & 1;
-#pragma unroll
-            for (int r = 0; r < TR; ++r) {
-                const int y = y0 + r, x = x0 + m;
-                s_lab[r * TM + m] = (y < a.y_end && x < a.W) ? a.seg[(size_t)y * a.W + x] : -1;
-            }
-            mbar_wait(acc_full(buf), (it >> 1) & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int r = 0; r < TR; ++r) {
-                float bat[Bk::NBATT];
-#pragma unroll
-                for (int b = 0; b < Bk::NBATT; ++b) bat[b] = -INFINITY;
-#pragma unroll
-                for (int c = 0; c < NPAD / 16; ++c) {
-                    if (16 * c >= Bk::GS * Bk::NG + Bk::NS) continue;       // padding columns only
-                    float v[16];
-                    tmem_ld16(tbase + ((uint32_t)(32 * q) << 16) + buf * (TR * NPAD) + r * NPAD + 16 * c, v);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int b = lm_batt_of_col<NPAD>(16 * c + j);
-                        if (b >= 0) bat[b] = fmaxf(bat[b], v[j]);
-                    }
-                }
-#pragma unroll
-                for (int b = 0; b < Bk::NBATT; ++b) T[(r * TM + m) * Sm::TS + b] = fminf(bat[b], 1.e6f);   // MAX_SIGNAL_RESPONSE
-            }
-            tc_fence_before();
-            mbar_arrive(acc_empty(buf));                                    // the tile after next may overwrite this accumulator buffer
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (walker) {
-                // one (output row, battery) pair and half a row per thread: run-length sums along x, flushed when the label changes
-                const size_t fstride = (size_t)a.n_batt * 3;
-                double s1 = 0.0, s2 = 0.0;
-                int cur = -1;
-                const int* lab = s_lab + wr * TM + half * (TM / 2);
-                const float* tv = T + (size_t)(wr * TM + half * (TM / 2)) * Sm::TS + wb;
-                for (int i = 0; i < TM / 2; ++i) {
-                    const int lb = lab[i];
-                    if (lb != cur) {
-                        if (cur >= 0) {
-                            atomicAdd(&a.S1[(size_t)cur * fstride + wb * 3 + ch], s1);
-                            atomicAdd(&a.S2[(size_t)cur * fstride + wb * 3 + ch], s2);
-                            g2 += s2;
-                        }
-                        cur = lb; s1 = 0.0; s2 = 0.0;
-                    }
-                    if (lb >= 0) { const double v = (double)tv[(size_t)i * Sm::TS]; s1 += v; s2 += v * v; }
-                }
-                if (cur >= 0) {
-                    atomicAdd(&a.S1[(size_t)cur * fstride + wb * 3 + ch], s1);
-                    atomicAdd(&a.S2[(size_t)cur * fstride + wb * 3 + ch], s2);
-                    g2 += s2;
-                }
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
-        if (walker && g2 != 0.0) atomicAdd(&a.G2[wb], g2);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tbase, 512);
-}
-
-// ---- the same contraction, re-cut for what the tensor core actually charges ---------------------------------------------------------
-// Measured on B200 (scripts/dev_umma_rate.py, profiles/r02_umma_rate.md): a tcgen05.mma kind::tf32 of M 128 x K 8 costs
-//   max(~104, N/2 + 43) clocks with A in shared memory,  max(~104, N/2 + 10) clocks with A in tensor memory
-// -- a floor of ~104 clocks per instruction whatever N is.  The first tcgen05 version above issues N = 80 instructions (ideal 40
-// clocks) and sits on that floor: 1485 instructions per tile, tensor pipe 57 % busy.  This version
+// How the instruction stream is cut, and why.  Measured on B200 (scripts/dev_umma_rate.py, profiles/r02_lm_tcgen05.md): a tcgen05.mma
+// kind::tf32 of M 128 x K 8 costs  max(~104, N/2 + 43) clocks with A in shared memory,  max(~104, N/2 + 10) with A in tensor memory:
+// a floor of ~104 clocks per instruction whatever N is, and 4 KB of A per instruction is more than shared memory can feed beside B.
+// The first tcgen05 version of this kernel (one N = 80 instruction per output row, both operands in shared memory, 1485 instructions
+// per tile) ran 12.4 ms per 2048 x 2048 image with the tensor pipe 57 % busy.  This one
 //   * keeps the patch matrices A_s (value and remainder, 2 x 40 columns, lane = pixel) in TENSOR MEMORY: the producers write them
 //     with tcgen05.st, the instruction reads only the weights from shared memory;
 //   * runs the three output rows of a tile as ONE instruction of N = 3 x NPAD: A_s is the same for them, their accumulators are
@@ -443,7 +239,7 @@ template <int NPAD> struct LmTs {
     static constexpr int OFF_T = OFF_RAW + NRAW * 2 * RAW_PITCH;
     static constexpr int OFF_LAB = OFF_T + TR * TM * TS * 4;
     static constexpr int OFF_BAR = OFF_LAB + TR * TM * 4;
-    static constexpr int N_BAR = 2 * NRAW + 2 * NAT + 2 * NBT + 2 * NACC;
+    static constexpr int N_BAR = 2 * NRAW + 2 * NAT + 2 * NBT + NACC + NACC * TR;
     static constexpr int OFF_TMEM = OFF_BAR + N_BAR * 8;
     static constexpr int BYTES = OFF_TMEM + 16;
     static_assert(NAT >= 2, "tensor memory budget: at least two patch-matrix stages");
@@ -470,7 +266,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_lm_conv_ts(const __grid_const
     auto b_full = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + 2 * NAT + i); };
     auto b_empty = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + 2 * NAT + NBT + i); };
     auto acc_full = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + 2 * NAT + 2 * NBT + i); };
-    auto acc_empty = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + 2 * NAT + 2 * NBT + NACC + i); };
+    auto acc_empty = [&](uint32_t i) { return bar0 + 8u * (2 * NRAW + 2 * NAT + 2 * NBT + NACC + i); };   // one per (buffer, output row)
     uint32_t* tmem_slot = (uint32_t*)(smem + Sm::OFF_TMEM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -478,7 +274,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_lm_conv_ts(const __grid_const
         for (int i = 0; i < NRAW; ++i) { mbar_init(raw_full(i), 1); mbar_init(raw_empty(i), LM_PROD / 32); }
         for (int i = 0; i < NAT; ++i) { mbar_init(a_full(i), LM_PROD / 32); mbar_init(a_empty(i), 1); }
         for (int i = 0; i < NBT; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
-        for (int i = 0; i < NACC; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), TM); }
+        for (int i = 0; i < NACC; ++i) mbar_init(acc_full(i), 1);
+        for (int i = 0; i < NACC * TR; ++i) mbar_init(acc_empty(i), TM);
         fence_mbar_init();
         prefetch_tmap(&tmap);
     }
@@ -493,36 +290,38 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_lm_conv_ts(const __grid_const
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer ------------------------------------------------
-        if (lane == 0) {
-            uint32_t jr = 0, jb = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int ch = t / tiles_per_ch, rem = t - ch * tiles_per_ch;
-                const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-                const int x0 = tx * TM, y0 = a.y_first + ty * TR;
-                for (int s = 0; s < SROWS; ++s) {
-                    if (s < KW) {
-                        // kernel row s: 2 x KC pieces of NPAD filters x 4 taps, each to its k-chunk's ring (and to the mirror slot)
-                        const uint32_t slot = jb % NBT, ph = (jb / NBT) & 1;
-                        const bool mirror = slot < TR - 1;
-                        mbar_wait(b_empty(slot), ph ^ 1);
-                        mbar_arrive_expect_tx(b_full(slot), (mirror ? 2 : 1) * Sm::B_SLICE);
-                        const float* src = a.w_tc + (size_t)s * (Sm::B_SLICE / 4);
-#pragma unroll 1
-                        for (int c = 0; c < 2 * KC; ++c) {
-                            const uint32_t dst = sbase + Sm::OFF_B + (uint32_t)c * Sm::B_LBO + slot * Sm::SLOTC;
-                            bulk_g2s(dst, src + (size_t)c * (Sm::SLOTC / 4), Sm::SLOTC, b_full(slot));
-                            if (mirror) bulk_g2s(dst + NBT * Sm::SLOTC, src + (size_t)c * (Sm::SLOTC / 4), Sm::SLOTC, b_full(slot));
-                        }
-                        ++jb;
+        // the whole warp: lane c < 2 KC copies piece c of a weight slice (every lane issues its own cp.async.bulk in one warp
+        // instruction -- one thread issuing all twenty was the busiest thread of the CTA), two more lanes load the source row
+        uint32_t jr = 0, jb = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int ch = t / tiles_per_ch, rem = t - ch * tiles_per_ch;
+            const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+            const int x0 = tx * TM, y0 = a.y_first + ty * TR;
+            for (int s = 0; s < SROWS; ++s) {
+                if (s < KW) {
+                    // kernel row s: 2 x KC pieces of NPAD filters x 4 taps, each to its k-chunk's ring (and to the mirror slot)
+                    const uint32_t slot = jb % NBT, ph = (jb / NBT) & 1;
+                    const bool mirror = slot < TR - 1;
+                    mbar_wait(b_empty(slot), ph ^ 1);
+                    if (lane == 0) mbar_arrive_expect_tx(b_full(slot), (mirror ? 2 : 1) * Sm::B_SLICE);
+                    __syncwarp();
+                    if (lane < 2 * KC) {
+                        const float* src = a.w_tc + (size_t)s * (Sm::B_SLICE / 4) + (size_t)lane * (Sm::SLOTC / 4);
+                        const uint32_t dst = sbase + Sm::OFF_B + (uint32_t)lane * Sm::B_LBO + slot * Sm::SLOTC;
+                        bulk_g2s(dst, src, Sm::SLOTC, b_full(slot));
+                        if (mirror) bulk_g2s(dst + NBT * Sm::SLOTC, src, Sm::SLOTC, b_full(slot));
                     }
-                    const uint32_t slot = jr % NRAW, ph = (jr / NRAW) & 1;
-                    mbar_wait(raw_empty(slot), ph ^ 1);
-                    mbar_arrive_expect_tx(raw_full(slot), 2 * RAWW * 4);
-                    const uint32_t dst = sbase + Sm::OFF_RAW + slot * 2 * RAW_PITCH;
-                    tma_load_2d(dst, &tmap, x0, ch * a.Hp + y0 + s, raw_full(slot));
-                    tma_load_2d(dst + RAW_PITCH, &tmap, x0, (3 + ch) * a.Hp + y0 + s, raw_full(slot));
-                    ++jr;
+                    ++jb;
                 }
+                const uint32_t slot = jr % NRAW, ph = (jr / NRAW) & 1;
+                mbar_wait(raw_empty(slot), ph ^ 1);
+                if (lane == 0) mbar_arrive_expect_tx(raw_full(slot), 2 * RAWW * 4);
+                __syncwarp();
+                if (lane < 2) {
+                    const uint32_t dst = sbase + Sm::OFF_RAW + slot * 2 * RAW_PITCH + lane * RAW_PITCH;
+                    tma_load_2d(dst, &tmap, x0, (3 * lane + ch) * a.Hp + y0 + s, raw_full(slot));
+                }
+                ++jr;
             }
         }
     } else if (warp == 1) {
@@ -531,13 +330,14 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_lm_conv_ts(const __grid_const
             uint32_t jr = 0, jb_base = 0, it = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
                 const uint32_t buf = it % NACC;
-                mbar_wait(acc_empty(buf), ((it / NACC) & 1) ^ 1);
-                tc_fence_after();
                 const uint32_t acc0 = tbase + buf * (TR * NPAD);
                 for (int s = 0; s < SROWS; ++s) {
                     const uint32_t st = jr % NAT;
                     if (s < KW) { const uint32_t jb = jb_base + s; mbar_wait(b_full(jb % NBT), (jb / NBT) & 1); }
                     mbar_wait(a_full(st), (jr / NAT) & 1);
+                    // source row s < TR is the first to touch the accumulator of output row s: the epilogue hands the rows of the
+                    // previous tile back one by one, so the first instructions of this tile overlap its reading of the later rows
+                    if (s < TR) mbar_wait(acc_empty(buf * TR + s), ((it / NACC) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t a_hi = tbase + Sm::A_COL0 + st * (2 * KPAD), a_lo = a_hi + KPAD;
                     // output rows r_lo..r_hi take this source row with kernel rows dy = s - r; ascending dy = ascending slot = descending r,
@@ -640,9 +440,9 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_lm_conv_ts(const __grid_const
                 }
 #pragma unroll
                 for (int b = 0; b < Bk::NBATT; ++b) T[(r * TM + m) * Sm::TS + b] = fminf(bat[b], 1.e6f);   // MAX_SIGNAL_RESPONSE
+                tc_fence_before();
+                mbar_arrive(acc_empty(buf * TR + r));                       // this row's accumulator is in shared memory: the next tile may use it
             }
-            tc_fence_before();
-            mbar_arrive(acc_empty(buf));                                    // the accumulators are in shared memory: the next tile may start
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (walker) {
                 // one (output row, battery) pair and half a row per thread: run-length sums along x, flushed when the label changes
@@ -767,14 +567,6 @@ static size_t carve_lm(LmWs& w, void* ws, size_t bytes, int H, int W, int nb, in
     return isb_align(c.off);
 }
 
-// ISB_LM_OPERANDS=smem keeps both operands of the contraction in shared memory (the first tcgen05 version, kept for A/B timing)
-static bool lm_a_in_tmem()
-{
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("ISB_LM_OPERANDS"); v = (e && !strcmp(e, "smem")) ? 0 : 1; }
-    return v == 1;
-}
-
 template <int NPAD>
 static int launch_lm_conv(const CUtensorMap& tmap, const LmTcArgs& a, int n_tiles, cudaStream_t st)
 {
@@ -782,13 +574,8 @@ static int launch_lm_conv(const CUtensorMap& tmap, const LmTcArgs& a, int n_tile
     ISB_CUDA_CHECK(cudaGetDevice(&dev));
     ISB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = n_tiles < sms ? n_tiles : sms;   // persistent: one CTA per SM, tiles round-robin
-    if (lm_a_in_tmem()) {
-        ISB_CUDA_CHECK(cudaFuncSetAttribute(k_lm_conv_ts<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmTs<NPAD>::BYTES));
-        k_lm_conv_ts<NPAD><<<grid, LM_THREADS, LmTs<NPAD>::BYTES, st>>>(tmap, a);
-    } else {
-        ISB_CUDA_CHECK(cudaFuncSetAttribute(k_lm_conv_tc<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmSmem<NPAD>::BYTES));
-        k_lm_conv_tc<NPAD><<<grid, LM_THREADS, LmSmem<NPAD>::BYTES, st>>>(tmap, a);
-    }
+    ISB_CUDA_CHECK(cudaFuncSetAttribute(k_lm_conv_ts<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmTs<NPAD>::BYTES));
+    k_lm_conv_ts<NPAD><<<grid, LM_THREADS, LmTs<NPAD>::BYTES, st>>>(tmap, a);
     ISB_LAUNCH_CHECK();
     return ISB_OK;
 }
@@ -804,17 +591,12 @@ static int lm_accumulate(const void* img, int dtype, const int32_t* seg, int H, 
     Mix3 mix;
     for (int i = 0; i < 9; ++i) mix.m[i] = chmix_host[i];
     if (bg_radius > 0) {
-        const size_t smem = sizeof(double) * (2 * (size_t)(bg_radius + VB_R) + 1);
-        ISB_REQUIRE(smem <= 200 * 1024, "background radius too large");
-        ISB_CUDA_CHECK(cudaFuncSetAttribute(k_lm_vblur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // axis 0 (rows): p0 [3][H][W] -> p1
-        k_lm_vblur<<<dim3((W + 2 * VB_T - 1) / (2 * VB_T), (H + VB_R - 1) / VB_R, 3), VB_T, smem, st>>>(w.p0, H, W, bg_weights, bg_radius, w.p1);
-        ISB_LAUNCH_CHECK();
+        if (int rc = launch_vblur(w.p0, H, W, bg_weights, bg_radius, w.p1, st)) return rc;
         // axis 1 (cols): transpose, blur along the (new) rows axis; the result stays transposed [3][W][H]
         k_lm_transpose<<<dim3((W + 31) / 32, (H + 31) / 32, 3), 256, 0, st>>>(w.p1, H, W, w.p2);
         ISB_LAUNCH_CHECK();
-        k_lm_vblur<<<dim3((H + 2 * VB_T - 1) / (2 * VB_T), (W + VB_R - 1) / VB_R, 3), VB_T, smem, st>>>(w.p2, W, H, bg_weights, bg_radius, w.p1);
-        ISB_LAUNCH_CHECK();
+        if (int rc = launch_vblur(w.p2, W, H, bg_weights, bg_radius, w.p1, st)) return rc;
     } else {
         ISB_CUDA_CHECK(cudaMemsetAsync(w.p1, 0, sizeof(double) * 3 * npx, st));
     }

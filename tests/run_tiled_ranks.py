@@ -44,6 +44,17 @@ def main():
     full, _, _ = pipe_color2d_slic_features_model_graphcut_tiled(img, 3, {'color': ['mean']}, sp_size=20, sp_regul=0.2, comm=comm,
                                                                 want_soft=False, gather_segm=True)
     assert np.array_equal(full, segm)
+    # Leung-Malik statistics over the bands (each rank: its rows + 616 rows of halo; sums and response norms all-reduced) against the
+    # whole-image descriptor this rank computes on its own GPU
+    from pyimsegm_b200.texture import device_lm_features
+    from pyimsegm_b200.tiled import LM_ROW_MARGIN, texture_stats_tiled
+    img = synth_regions(2600, 160, seed=33)[0] + 0.05 * np.random.RandomState(3).standard_normal((2600, 160, 3))
+    n_seg, compact = slic_params(img.shape[:2], 24, 0.2)
+    res = slic_tiled(img, n_seg, compact, comm=comm, eng=eng, raw_margin=LM_ROW_MARGIN)
+    flags = ('mean', 'std', 'energy')
+    got = eng.to_host(texture_stats_tiled(res, img.dtype, flags, 'short', comm=comm, eng=eng)).copy()
+    want = eng.to_host(device_lm_features(eng, eng.to_device(img, 'image'), res.d_seg, int(res.nb_bound), flags, 'short')[0]).copy()
+    np.testing.assert_allclose(got, want, rtol=1e-7, atol=1e-9)
     ok = torch.ones(1, device='cuda')
     dist.all_reduce(ok)
     if comm.rank == 0 and int(ok.item()) == comm.world:
