@@ -258,47 +258,54 @@ __global__ void __launch_bounds__(256) k_row_assign_labels(int H, int W, const i
     }
 }
 
-// one thread per small piece: replay its BFS, remember the last foreign earlier-labelled neighbour piece
-__global__ void k_small_adjacent(int H, int W, int* comp, const int* __restrict__ size, int max_size,
-                                 const int* __restrict__ list, int* ctr, int* aux, int* queue)
+// one thread per small piece: replay its BFS, remember the last foreign earlier-labelled neighbour piece.
+// The kernel is a chain of dependent loads per piece (queue entry -> four neighbours), as long as the largest small piece: the queue of
+// a piece (fewer than min_size entries) lives in SHARED memory when it fits (SQ: 32 threads per CTA, entry j of lane l at q[32 j + l]),
+// which takes one of the two global round trips out of every BFS step.
+template <bool SQ>
+__global__ void __launch_bounds__(SQ ? 32 : 256) k_small_adjacent(int H, int W, int* comp, const int* __restrict__ size, int max_size,
+                                                                   const int* __restrict__ list, int* ctr, int* aux, int* queue)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ctr[1]) return;
-    const int C = list[i];
-    int* q = queue + atomicAdd(&ctr[2], size[C]);
-    int adjacent = -1;
-    q[0] = C;
-    // the visited flag lives in comp[] itself (only this thread writes the pixels of its own piece; every reader masks the
-    // flag with dec()), so one round of four independent loads per BFS step is all the memory latency there is
-    comp[C] = (comp[C] < 0 ? ~(dec(comp[C]) | VISBIT) : (comp[C] | VISBIT));
-    int n = 1, v = 0;
-    while (v < n && n < max_size) {
-        const int cp = q[v];
-        const int cy = cp / W, cx = cp - cy * W;
-        // the four neighbours in the original's order (+x, -x, +y, -y)
-        const int np4[4] = { cx + 1 < W ? cp + 1 : -1, cx > 0 ? cp - 1 : -1, cy + 1 < H ? cp + W : -1, cy > 0 ? cp - W : -1 };
-        int raw4[4];
+    extern __shared__ int s_q[];
+    const int n_small = ctr[1];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_small; i += gridDim.x * blockDim.x) {
+        const int C = list[i];
+        int* q = SQ ? s_q + threadIdx.x : queue + atomicAdd(&ctr[2], size[C]);
+        constexpr int QS = SQ ? 32 : 1;
+        int adjacent = -1;
+        q[0] = C;
+        // the visited flag lives in comp[] itself (only this thread writes the pixels of its own piece; every reader masks the
+        // flag with dec()), so one round of four independent loads per BFS step is all the memory latency there is
+        comp[C] = (comp[C] < 0 ? ~(dec(comp[C]) | VISBIT) : (comp[C] | VISBIT));
+        int n = 1, v = 0;
+        while (v < n && n < max_size) {
+            const int cp = q[v * QS];
+            const int cy = cp / W, cx = cp - cy * W;
+            // the four neighbours in the original's order (+x, -x, +y, -y)
+            const int np4[4] = { cx + 1 < W ? cp + 1 : -1, cx > 0 ? cp - 1 : -1, cy + 1 < H ? cp + W : -1, cy > 0 ? cp - W : -1 };
+            int raw4[4];
 #pragma unroll
-        for (int d = 0; d < 4; ++d) raw4[d] = np4[d] >= 0 ? comp[np4[d]] : 0;
+            for (int d = 0; d < 4; ++d) raw4[d] = np4[d] >= 0 ? comp[np4[d]] : 0;
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            if (np4[d] < 0) continue;
-            const int raw = raw4[d];
-            const int r = dec(raw);
-            if (r == C) {
-                const bool seen = ((raw < 0 ? ~raw : raw) & VISBIT) != 0; // the four neighbours of one pixel are distinct
-                if (!seen) {
-                    comp[np4[d]] = raw < 0 ? ~((~raw) | VISBIT) : (raw | VISBIT);
-                    q[n++] = np4[d];
-                    if (n >= max_size) break;
+            for (int d = 0; d < 4; ++d) {
+                if (np4[d] < 0) continue;
+                const int raw = raw4[d];
+                const int r = dec(raw);
+                if (r == C) {
+                    const bool seen = ((raw < 0 ? ~raw : raw) & VISBIT) != 0; // the four neighbours of one pixel are distinct
+                    if (!seen) {
+                        comp[np4[d]] = raw < 0 ? ~((~raw) | VISBIT) : (raw | VISBIT);
+                        q[(n++) * QS] = np4[d];
+                        if (n >= max_size) break;
+                    }
+                } else if (r < C) {
+                    adjacent = r;
                 }
-            } else if (r < C) {
-                adjacent = r;
             }
+            ++v;
         }
-        ++v;
+        aux[C] = adjacent >= 0 ? -2 - adjacent : -1; // small roots store -2-adjacent (kept roots store label >= 0)
     }
-    aux[C] = adjacent >= 0 ? -2 - adjacent : -1; // small roots store -2-adjacent (kept roots store label >= 0)
 }
 
 __global__ void k_write_labels(int n, const int* __restrict__ comp, const int* __restrict__ size, int min_size,
@@ -379,9 +386,21 @@ extern "C" int isb_enforce_connectivity(const int32_t* labels, int H, int W, int
     ISB_LAUNCH_CHECK();
     k_row_assign_labels<<<H, 256, 0, st>>>(H, W, comp, w.size, min_size, w.row_cnt, aux, w.list, w.ctr);
     ISB_LAUNCH_CHECK();
-    // upper bound on the number of small roots is n; launch enough threads, the kernel reads the real count
-    k_small_adjacent<<<nb, 256, 0, st>>>(H, W, comp, w.size, max_size, w.list, w.ctr, aux, w.queue);
-    ISB_LAUNCH_CHECK();
+    // the kernel reads the real count of small roots and strides over them
+    {
+        int dev = 0, sms = 0;
+        ISB_CUDA_CHECK(cudaGetDevice(&dev));
+        ISB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (min_size >= 1 && min_size <= 512) {
+            // a small piece has fewer than min_size pixels: its queue fits min_size entries of shared memory per thread
+            const size_t smem = sizeof(int) * 32 * (size_t)min_size;
+            ISB_CUDA_CHECK(cudaFuncSetAttribute(k_small_adjacent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_small_adjacent<true><<<sms * 16, 32, smem, st>>>(H, W, comp, w.size, max_size, w.list, w.ctr, aux, w.queue);
+        } else {
+            k_small_adjacent<false><<<sms * 8, 256, 0, st>>>(H, W, comp, w.size, max_size, w.list, w.ctr, aux, w.queue);
+        }
+        ISB_LAUNCH_CHECK();
+    }
     k_write_labels<<<nb, 256, 0, st>>>(n, comp, w.size, min_size, aux, out);
     ISB_LAUNCH_CHECK();
     return ISB_OK;
