@@ -129,6 +129,17 @@ def load_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
+def load_tensor_peak():
+    """(dense bf16 TFLOP/s, source) -- the tensor-core denominator: MEASURED_PEAKS.json's burst figure, else the profiling guide's"""
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        if 'bf16_tflops' in p:
+            return float(p['bf16_tflops']), 'measured (MEASURED_PEAKS.json bf16_tflops, burst)'
+    return 1590.0, 'fallback (B200_PROFILING.md 1.59 PFLOP/s)'
+
+
 TRAFFIC_SOURCE = 'profiles/r02c_assign_traffic.json'
 
 
@@ -622,14 +633,27 @@ def run_texture(args):
                         'd2h_bytes_per_step': int(segm.nbytes + soft.nbytes)},
                 'features_only': {'value': world * args.steps * mpix / (ms_f / 1e3), 'unit': 'MPix/s', 'ms_per_step': ms_f / args.steps,
                                   'note': 'compute_color2d_superpixels_features: SLIC + colour + LM descriptors, host in / host out'},
-                'roofline': {'kernel': 'k_lm_conv_tc (lm_texture)', 'bound': 'tensor', 'unit': 'TFLOP/s',
-                             'achieved': 3 * 76 * 33 * 33 * 2 * H * W / (lm / 1e3) / 1e12 if lm > 0 else None,
-                             'note': 'algorithmic flops (one multiply-add per tap) over the whole lm_texture stage (background pass included); the '
-                                     'tcgen05 contraction alone: profiles/r02_lm_tcgen05.md'},
+                'roofline': lm_roofline(lm, H, W),
                 'gpu_launches': int(launches), 'stages': stages}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def lm_roofline(lm_ms, H, W):
+    """tensor-bound roofline of the Leung-Malik stage: algorithmic flops = one multiply-add per tap (3 channels x 76 kernels x 33^2 x 2
+    per pixel); executed = what the tcgen05 contraction issues (76 -> 80 filters, 33 -> 40 taps per kernel row, three TF32
+    products per multiply)"""
+    if not lm_ms:
+        return None
+    peak, peak_source = load_tensor_peak()
+    algo = 3 * 76 * 33 * 33 * 2 * H * W / (lm_ms / 1e3) / 1e12
+    executed = 3 * 80 * 33 * 40 * 2 * 3 * H * W / (lm_ms / 1e3) / 1e12
+    return {'kernel': 'k_lm_conv_ts (lm_texture stage: FP64 background blur + tcgen05 contraction + fused statistics)', 'bound': 'tensor',
+            'unit': 'TFLOP/s', 'achieved': algo, 'peak': peak, 'frac': algo / peak, 'peak_source': peak_source,
+            'executed_tf32': executed, 'executed_frac_of_tf32_peak': executed / (peak / 2),
+            'note': 'achieved = algorithmic flops over the WHOLE lm_texture stage time (CUDA events); peak = measured dense bf16 (TF32 runs '
+                    'at half of it); the contraction kernel alone and its ncu capture: profiles/r02_lm_tcgen05.md'}
 
 
 def run_rg2sp(args):
