@@ -864,14 +864,48 @@ __global__ void __launch_bounds__(1024) k_big_chol(int N_in, const int* n_dev, i
         if (tid == 0) { w.state[init * 4 + 1] = 1.0; w.state[init * 4 + 3] = 1.0; } // done, failed
         return;
     }
-    // reciprocals of the diagonal (the forward substitution below multiplies instead of dividing 189 times per column)
-    for (int j = tid; j < D; j += T) s_col[j] = 1.0 / Ls[idx(j, j)];
+    // log|prec_chol| + log weight; the factor goes to global memory (the slot of this pair's first Gram partial, which is dead now) for
+    // the inversion kernel, which spreads the independent columns of L^-1 over several CTAs
+    double* Lg = w.gram + ((size_t)init * K + k) * KS * D * D;
+    for (int i = tid; i < D * (D + 1) / 2; i += T) Lg[i] = Ls[i];
+    if (wid == 0) {
+        double ld = 0;
+        for (int j = lane; j < D; j += 32) ld -= log(Ls[j * (j + 1) / 2 + j]);
+        s_ld[lane] = ld;
+        __syncwarp();
+        if (lane == 0) {
+            double t = 0;
+            for (int i = 0; i < 32; ++i) t += s_ld[i];
+            w.ldw[init * K + k] = t + log(nk / N);
+        }
+    }
+    __syncthreads();   // every thread has read nk = wts[k]
+    if (tid == 0) wts[k] = nk / N;
+}
+
+// prec_chol = (L^-1)^T of one (restart, component) pair, the columns of Z = L^-1 dealt round-robin to CHOL_SPLIT CTAs x 32 warps:
+//     Z[c][c] = 1 / L[c][c],   Z[r][c] = -(sum_{p=c}^{r-1} L[r][p] Z[p][c]) / L[r][r]   (r > c)
+// forward substitution, one warp per column c with the column in registers (lane l holds Z[c + l + 32 q][c]).  Column c of Z is row c of
+// U (upper triangular); the warp writes the whole row, zeros below the diagonal included (the E-step multiplies by the whole matrix).
+constexpr int CHOL_SPLIT = 4;
+__global__ void __launch_bounds__(1024) k_big_inv(int D, int K, GmmWs w)
+{
+    extern __shared__ double Ls[];
+    const int k = blockIdx.x, init = blockIdx.y, part = blockIdx.z;
+    if (w.state[init * 4 + 1] != 0.0) return;
+    double* par = w.par + (size_t)init * pstride(K, D);
+    double* U = par + K + K * D + (size_t)K * D * D + (size_t)k * D * D;
+    const double* Lg = w.gram + ((size_t)init * K + k) * KS * D * D;
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+    __shared__ double s_col[DBIG];
+    for (int i = tid; i < D * (D + 1) / 2; i += T) Ls[i] = Lg[i];
     __syncthreads();
-    // Z = L^-1 (lower) by forward substitution, one warp per column c, the column in registers (lane l holds Z[c + l + 32 q][c]):
-    //     Z[c][c] = 1 / L[c][c],   Z[r][c] = -(sum_{p=c}^{r-1} L[r][p] Z[p][c]) / L[r][r]   (r > c)
-    // prec_chol = Z^T: column c of Z is row c of U.
+    // reciprocals of the diagonal (the forward substitution multiplies instead of dividing 189 times per column)
+    for (int j = tid; j < D; j += T) s_col[j] = 1.0 / Ls[j * (j + 1) / 2 + j];
+    __syncthreads();
     constexpr int ZQ = (DBIG + 31) / 32;
-    for (int c = wid; c < D; c += nw) {
+    for (int c = wid * CHOL_SPLIT + part; c < D; c += nw * CHOL_SPLIT) {
         double z[ZQ];
 #pragma unroll
         for (int q = 0; q < ZQ; ++q) z[q] = 0.0;
@@ -891,29 +925,24 @@ __global__ void __launch_bounds__(1024) k_big_chol(int N_in, const int* n_dev, i
 #pragma unroll
             for (int q = 0; q < ZQ; ++q) if (q == slot && lane == owner) z[q] = val;
         }
+        for (int pp = lane; pp < c; pp += 32) U[(size_t)c * D + pp] = 0.0;
 #pragma unroll
         for (int q = 0; q < ZQ; ++q) {
             const int pp = c + lane + 32 * q;
             if (pp < D) U[(size_t)c * D + pp] = z[q];
         }
     }
-    // zero below the diagonal (the E-step multiplies by the whole matrix)
-    for (int i = tid; i < D * D; i += T) { const int a = i / D, b = i % D; if (a > b) U[i] = 0.0; }
-    // log|prec_chol| + log weight
-    if (wid == 0) {
-        double ld = 0;
-        for (int j = lane; j < D; j += 32) ld -= log(Ls[j * (j + 1) / 2 + j]);
-        s_ld[lane] = ld;
-        __syncwarp();
-        if (lane == 0) {
-            double t = 0;
-            for (int i = 0; i < 32; ++i) t += s_ld[i];
-            w.ldw[init * K + k] = t + log(nk / N);
-        }
-    }
-    __syncthreads();   // U complete (global memory, visible to the whole CTA)
-    // mu U: four lanes per column, each over a quarter of the rows
-    for (int j4 = tid; j4 < 4 * ((D + 7) / 8) * 8; j4 += T) {
+}
+
+// b = mu U of every (restart, component): four lanes per column, each over a quarter of the rows
+__global__ void __launch_bounds__(1024) k_big_bvec(int D, int K, GmmWs w)
+{
+    const int k = blockIdx.x, init = blockIdx.y;
+    if (w.state[init * 4 + 1] != 0.0) return;
+    const double* par = w.par + (size_t)init * pstride(K, D);
+    const double* mu = par + K + (size_t)k * D;
+    const double* U = par + K + K * D + (size_t)K * D * D + (size_t)k * D * D;
+    for (int j4 = threadIdx.x; j4 < 4 * ((D + 7) / 8) * 8; j4 += blockDim.x) {
         const int j = j4 >> 2, part = j4 & 3;
         double a = 0;
         if (j < D)
@@ -922,7 +951,6 @@ __global__ void __launch_bounds__(1024) k_big_chol(int N_in, const int* n_dev, i
         a += __shfl_xor_sync(0xffffffffu, a, 2);
         if (j < D && part == 0) w.bvec[((size_t)init * K + k) * D + j] = a;
     }
-    if (tid == 0) wts[k] = nk / N;
 }
 
 // E-step after the GEMM: warp per sample; log N_k from |Y[r,k][n] - b[r,k]|^2, responsibilities, per-block log-likelihood sums
@@ -1051,6 +1079,7 @@ static int fit_big(int N, const int* n_dev, int D, int K, int n_init, int max_it
     const int ps = pstride(K, D);
     const size_t chol_smem = sizeof(double) * (size_t)D * (D + 1) / 2;
     ISB_CUDA_CHECK(cudaFuncSetAttribute(k_big_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
+    ISB_CUDA_CHECK(cudaFuncSetAttribute(k_big_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
     auto m_step = [&]() -> int {
         k_big_means<<<dim3(K, n_init, (D + 31) / 32), 1024, 0, st>>>(N, n_dev, D, K, w);
         ISB_LAUNCH_CHECK();
@@ -1063,6 +1092,10 @@ static int fit_big(int N, const int* n_dev, int D, int K, int n_init, int max_it
             ISB_LAUNCH_CHECK();
         }
         k_big_chol<<<dim3(K, n_init), 1024, chol_smem, st>>>(N, n_dev, D, K, reg, w);
+        ISB_LAUNCH_CHECK();
+        k_big_inv<<<dim3(K, n_init, CHOL_SPLIT), 1024, chol_smem, st>>>(D, K, w);
+        ISB_LAUNCH_CHECK();
+        k_big_bvec<<<dim3(K, n_init), 1024, 0, st>>>(D, K, w);
         ISB_LAUNCH_CHECK();
         return ISB_OK;
     };
