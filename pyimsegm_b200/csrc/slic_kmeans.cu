@@ -405,13 +405,17 @@ __global__ void __launch_bounds__(ATHREADS, 5) k_assign(const __grid_constant__ 
 // member lies within 2*step rows of the centre the assignment used, i.e. inside that band's slab -- checked, violations are
 // counted in xchg[6n]); the result goes to the exchange record xchg[6k..6k+5] = bits(cy, cx, c0, c1, c2), state (1 alive,
 // 2 died) and every other band leaves zeros there, so that an integer sum over the bands is an exact merge.
+// A warp's time is the length of its cluster's dependent chain, so the launch should be ONE wave: UWARPS warps per CTA and UBLOCKS CTAs
+// per SM give 148 x UWARPS x UBLOCKS resident warps -- with 2 x 17 that is 5 032, enough for the ~5 000 clusters of a 2048 x 2048 image at
+// sp_size 29 (8 x 4 = 4 736 left 5 % of the clusters for a second wave that cost as much as the first).
+constexpr int UWARPS = 2, UBLOCKS = 17;
 template <bool BAND>
-__global__ void __launch_bounds__(256) k_update(KmState s, const double* __restrict__ lab, const int* __restrict__ labels,
-                                                long long* __restrict__ xchg)
+__global__ void __launch_bounds__(32 * UWARPS, UBLOCKS) k_update(KmState s, const double* __restrict__ lab, const int* __restrict__ labels,
+                                                                 long long* __restrict__ xchg)
 {
-    __shared__ double buf[8][3][72];   // two 32-pixel chunks + the zero padding + one look-ahead group
+    __shared__ double buf[UWARPS][3][72];   // two 32-pixel chunks + the zero padding + one look-ahead group
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-    const int k = blockIdx.x * 8 + wl;
+    const int k = blockIdx.x * UWARPS + wl;
     if (k >= s.n) return;
     // the box of this cluster's members, gathered by k_assign (empty when the cluster has no pixel)
     const int4 o = s.obb[k];
@@ -675,7 +679,7 @@ extern "C" int isb_slic_kmeans(const double* lab_planar, int H, int W, const dou
             launch_assign(s, lab_map, use_tma, lab_planar, labels, st);
         }
         ISB_LAUNCH_CHECK();
-        { ProfScope p(ISB_PROF_UPDATE, st); k_update<false><<<(n_seeds + 7) / 8, 256, 0, st>>>(s, lab_planar, labels, nullptr); }
+        { ProfScope p(ISB_PROF_UPDATE, st); k_update<false><<<(n_seeds + UWARPS - 1) / UWARPS, 32 * UWARPS, 0, st>>>(s, lab_planar, labels, nullptr); }
         ISB_LAUNCH_CHECK();
         if (slic_zero) {
             const size_t npx = (size_t)H * W;
@@ -751,7 +755,7 @@ extern "C" int isb_slic_band_update(const isb_slic_band_t* b, int64_t* xchg, isb
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope p(ISB_PROF_UPDATE, st);
     ISB_CUDA_CHECK(cudaMemsetAsync(xchg, 0, sizeof(int64_t) * (6 * (size_t)s.n + 1), st));
-    k_update<true><<<(s.n + 7) / 8, 256, 0, st>>>(s, b->lab_slab, b->labels_slab, (long long*)xchg);
+    k_update<true><<<(s.n + UWARPS - 1) / UWARPS, 32 * UWARPS, 0, st>>>(s, b->lab_slab, b->labels_slab, (long long*)xchg);
     ISB_LAUNCH_CHECK();
     return ISB_OK;
 }
