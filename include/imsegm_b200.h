@@ -306,6 +306,8 @@ int isb_umma_selftest(const float* A, const float* B, int N, int K, int variant,
 /* profiling aid: clocks that `reps` back-to-back tcgen05.mma kind::tf32 instructions (M 128, K 8, the given N) take on each of `ctas`
  * CTAs; mode bit 0 = rotate over several accumulators, bit 1 = A operand from tensor memory.  cycles: device, [ctas] int64 */
 int isb_umma_rate(int N, int reps, int mode, int ctas, long long* cycles, isb_stream_t stream);
+/* profiling aid: clocks per dependent FP64 add / multiply / fma (one warp, chains of n operations); out: device, 4 doubles */
+int isb_fp64_latency(int n, double* out, isb_stream_t stream);
 
 /* per-segment, per-channel median -- numpy_img2d_color_median (imsegm/descriptors.py:420-455, channels = 3, n_px = H*W) and
  * numpy_img3d_gray_median (:651-676, channels = 1, n_px = D*H*W); np.median semantics (mean of the two middle values for an even

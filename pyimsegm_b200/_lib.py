@@ -79,6 +79,7 @@ SIGNATURES = {
     'isb_lm_texture': (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, C.POINTER(_d), _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _sz, _vp]),
     'isb_umma_selftest': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     'isb_umma_rate': (_i, [_i, _i, _i, _i, _vp, _vp]),
+    'isb_fp64_latency': (_i, [_i, _vp, _vp]),
     'isb_fill_i32': (_i, [_vp, _ll, _i, _vp]),
     'isb_combine': (_i, [_vp, _vp, _ll, _i, _vp]),
     'isb_gray_stats_workspace_bytes': (_sz, [_i]),

@@ -124,7 +124,31 @@ __global__ void __launch_bounds__(128) k_umma_rate(int N, int reps, int mode, lo
     if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
+// dependent-issue latency of the FP64 pipe: one warp, chains of n dependent operations; out[0..2] = clocks per DADD, DMUL, DFMA, out[3] = sink
+__global__ void k_fp64_latency(int n, double seed, double* out)
+{
+    double a = seed, b = seed * 0.5, c = seed * 0.25;
+    long long t0 = clock64();
+    for (int i = 0; i < n; ++i) a = __dadd_rn(a, seed);
+    long long t1 = clock64();
+    for (int i = 0; i < n; ++i) b = __dmul_rn(b, seed);
+    long long t2 = clock64();
+    for (int i = 0; i < n; ++i) c = __fma_rn(c, seed, seed);
+    long long t3 = clock64();
+    if (threadIdx.x == 0) {
+        out[0] = (double)(t1 - t0) / n; out[1] = (double)(t2 - t1) / n; out[2] = (double)(t3 - t2) / n; out[3] = a + b + c;
+    }
+}
+
 } // namespace
+
+extern "C" int isb_fp64_latency(int n, double* out, isb_stream_t stream)
+{
+    ISB_REQUIRE(out && n > 0, "bad arguments");
+    k_fp64_latency<<<1, 32, 0, (cudaStream_t)stream>>>(n, 1.0000001, out);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
 
 // dev / profiling aid: cycles[b] = clocks CTA b needed for `reps` instructions (see k_umma_rate); `ctas` CTAs run the same loop side by side
 extern "C" int isb_umma_rate(int N, int reps, int mode, int ctas, long long* cycles, isb_stream_t stream)

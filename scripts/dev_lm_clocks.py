@@ -38,5 +38,5 @@ rows = [l.strip().split(', ') for l in open('gpurun_out/lm_clocks.csv') if l.str
 rows = rows[6:-1]
 clk = np.array([float(r[0]) for r in rows]); pw = np.array([float(r[2]) for r in rows])
 print('%s: %d descriptors back to back, %.2f ms each; SM clock median %.0f MHz (min %.0f, max %.0f of %s), power median %.0f W (max %.0f); sw_power_cap active in %d of %d samples'
-      % (os.environ.get('ISB_LM_OPERANDS', 'tmem'), n, ms, np.median(clk), clk.min(), clk.max(), rows[0][1], np.median(pw), pw.max(),
+      % ('lm_texture', n, ms, np.median(clk), clk.min(), clk.max(), rows[0][1], np.median(pw), pw.max(),
          sum(r[3].strip() == 'Active' for r in rows), len(rows)))

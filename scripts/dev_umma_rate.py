@@ -19,3 +19,9 @@ for N in (16, 32, 48, 64, 80, 96, 128, 160, 192, 240, 256):
             cell.append(float(cyc.max()) / reps)
         row.append('%8.1f | %8.1f' % tuple(cell))
     print('%5d %22s %22s %22s %22s' % ((N,) + tuple(row)))
+out = torch.zeros(4, dtype=torch.float64, device='cuda')
+for _ in range(2):
+    _lib.check(lib.isb_fp64_latency(8192, _lib.ptr(out), _lib.stream_ptr()))
+torch.cuda.synchronize()
+o = out.cpu().numpy()
+print('dependent FP64 latency (clocks): add %.1f  mul %.1f  fma %.1f' % (o[0], o[1], o[2]))
