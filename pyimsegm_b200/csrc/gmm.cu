@@ -767,8 +767,8 @@ __global__ void __launch_bounds__(1024) k_big_means(int N_in, const int* n_dev, 
     }
 }
 
-// per (restart, component): covariance from the split-K Gram partials, Cholesky, prec_chol = (L^-1)^T, log-determinant + log
-// weight, b = mu U.  One CTA of 1024 threads; L lives in shared memory as a packed lower triangle (row i at i (i + 1) / 2).
+// per (restart, component): covariance from the split-K Gram partials, Cholesky factor (to global memory for k_big_inv), log-determinant
+// + log weight.  One CTA of 1024 threads; L lives in shared memory as a packed lower triangle (row i at i (i + 1) / 2).
 __global__ void __launch_bounds__(1024) k_big_chol(int N_in, const int* n_dev, int D, int K, double reg, GmmWs w)
 {
     extern __shared__ double Ls[];
@@ -776,16 +776,14 @@ __global__ void __launch_bounds__(1024) k_big_chol(int N_in, const int* n_dev, i
     if (w.state[init * 4 + 1] != 0.0) return;
     const int N = n_dev ? min(*n_dev, N_in) : N_in;
     double* par = w.par + (size_t)init * pstride(K, D);
-    double* wts = par; double* mu = par + K + (size_t)k * D;
+    double* wts = par;
     double* Cm = par + K + K * D + (size_t)k * D * D;                       // out: covariance
-    double* U = par + K + K * D + (size_t)K * D * D + (size_t)k * D * D;   // out: prec_chol (upper triangular)
     const double* G = w.gram + ((size_t)init * K + k) * KS * D * D;
     const int T = blockDim.x, tid = threadIdx.x;
     const int lane = tid & 31, wid = tid >> 5, nw = T >> 5;
     const double nk = wts[k];
     __shared__ int s_bad;
     __shared__ double s_ld[32];
-    __shared__ double s_col[DBIG];
     if (tid == 0) s_bad = 0;
     // covariance: the Gram partials are added in split order; only tiles on or above the diagonal were computed, so (a, b) with
     // a > b is read from (b, a)
@@ -797,7 +795,6 @@ __global__ void __launch_bounds__(1024) k_big_chol(int N_in, const int* n_dev, i
         const double c = g / nk + (a == b ? reg : 0.0);
         Cm[i] = c;
         if (b <= a) Ls[a * (a + 1) / 2 + b] = c;
-        else U[i] = 0.0;   // placeholder; the upper triangle is overwritten by Z^T below
     }
     __syncthreads();
     // blocked right-looking Cholesky on the packed lower triangle, panels of PB columns, three block-wide barriers per PANEL:

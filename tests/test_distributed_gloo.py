@@ -184,6 +184,15 @@ def test_plan_bands():
     assert (bands[0].km_lo, bands[0].raw_lo, bands[0].km_hi, bands[0].raw_hi) == (0, 0, 1083, 1087)
     assert (bands[3].km_lo, bands[3].raw_lo, bands[3].km_hi, bands[3].raw_hi) == (3013, 3009, 4155, 4159)
     assert bands[7].raw_hi == 8192
+    # without a margin the uploaded rows are the raw slab; a descriptor margin (Leung-Malik: 616 rows) widens them, clipped to the image
+    assert all((b.up_lo, b.up_hi) == (b.raw_lo, b.raw_hi) for b in bands)
+    wide = plan_bands(8192, 8, halo=59, radius=4, margin=616)
+    assert (wide[0].up_lo, wide[0].up_hi) == (0, 1024 + 616)
+    assert (wide[3].up_lo, wide[3].up_hi) == (3 * 1024 - 616, 4 * 1024 + 616)
+    assert (wide[7].up_lo, wide[7].up_hi) == (7 * 1024 - 616, 8192)
+    assert all((a.raw_lo, a.raw_hi, a.km_lo, a.km_hi) == (b.raw_lo, b.raw_hi, b.km_lo, b.km_hi) for a, b in zip(wide, bands))
+    small = plan_bands(900, 2, halo=59, radius=4, margin=616)       # the margin reaches past both ends: every band keeps the whole image
+    assert [(b.up_lo, b.up_hi) for b in small] == [(0, 900), (0, 900)]
     ragged = plan_bands(10, 3, halo=1, radius=0)
     assert [(b.own_lo, b.own_hi) for b in ragged] == [(0, 4), (4, 8), (8, 10)]
     with pytest.raises(ValueError):
