@@ -74,13 +74,10 @@ def _round_tf32(x):
     return out
 
 
-def _device_bank(bank_type):
-    """(names, d_w_tc, NP, orient, n_batt) for 'normal' / 'short', cached per device.  ``d_w_tc`` holds, per kernel row, the weights
-    in the operand layout of the tensor-core contraction (see isb_lm_texture): [33][hi|lo][10][NP/8][8][4] float32"""
-    eng = get_engine()
-    key = (bank_type, eng.device.index)
-    if key in _BANK_CACHE:
-        return _BANK_CACHE[key]
+def bank_operand_layout(bank_type):
+    """(names, w_tc, NP, orient, n_batt) for 'normal' / 'short' on the HOST.  ``w_tc`` holds, per kernel row, the weights in the operand
+    layout of the tensor-core contraction (see isb_lm_texture): float32 [33 kernel rows][hi | lo][10 k-chunks][NP / 8][8 filters][4 taps],
+    correlation form (kernels flipped), tf32-rounded value and tf32-rounded remainder, taps 33..39 and the padding filters zero"""
     from .descriptors import SHORT_FILTERS_SIGMAS
     if bank_type == 'short':
         filters, names = create_filter_bank_lm_2d(sigmas=SHORT_FILTERS_SIGMAS, nb_orient=4)
@@ -104,9 +101,18 @@ def _device_bank(bank_type):
     # [dy][dx][n] -> [dy][half][dx // 4][n // 8][n % 8][dx % 4]: K-major core matrices of 8 filters x 4 taps (16 bytes)
     both = np.stack([hi, lo], axis=1).reshape(_KW, 2, _KWP // 4, 4, NP // 8, 8)
     w_tc = np.ascontiguousarray(both.transpose(0, 1, 2, 4, 5, 3))
-    torch = eng.torch
-    d_w = torch.from_numpy(w_tc).to(eng.device)
-    _BANK_CACHE[key] = (names, d_w, NP, orient, len(filters))
+    return names, w_tc, NP, orient, len(filters)
+
+
+def _device_bank(bank_type):
+    """(names, d_w_tc, NP, orient, n_batt) for 'normal' / 'short', cached per device (:func:`bank_operand_layout` uploaded once)"""
+    eng = get_engine()
+    key = (bank_type, eng.device.index)
+    if key in _BANK_CACHE:
+        return _BANK_CACHE[key]
+    names, w_tc, NP, orient, n_batt = bank_operand_layout(bank_type)
+    d_w = eng.torch.from_numpy(w_tc).to(eng.device)
+    _BANK_CACHE[key] = (names, d_w, NP, orient, n_batt)
     return _BANK_CACHE[key]
 
 
